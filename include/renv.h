@@ -1,0 +1,140 @@
+/* renv.h -- C ABI of librenv_b200.so: the B200-native RandomCartPole-v0 / DR-sampler hot path.
+ *
+ * This is the drop-in boundary.  The reference (gabrieletiboni/random-envs) is pure Python and has
+ * no FFI; each entry point below names the Python method(s) of the reference it replaces
+ * (paths relative to the reference tree).  The shipped binding is ctypes
+ * (random_envs_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, PODs.  No C++/torch types, no exceptions, no global state.
+ *   - Every data pointer is a DEVICE pointer owned by the caller; the library never allocates,
+ *     frees or retains memory.  `renv_dr_cfg` / `renv_cartpole_env` are HOST structs read
+ *     during the call only.
+ *   - Work is enqueued on the caller's `cudaStream_t` (passed as void*); no host sync inside.
+ *   - Return value: 0 = OK; < 0 = invalid argument (enum renv_status); > 0 = cudaError_t of the launch.
+ *   - Alignment: `state`, `xi`, `reward`, `elapsed`, `out` 16 bytes; `action`, `done`, `truncated`,
+ *     `mask` 4 bytes; `ld` a multiple of 4 (f32) or 2 (f64).  Violations return RENV_E_ALIGN.
+ *   - Layout: structure-of-arrays.  `state` is (4, ld): rows x, x_dot, theta, theta_dot;
+ *     `xi` is (4, ld): rows gravity, cart_mass, pole_mass, pole_length
+ *     (order of random_envs/random_cartpole.py:104-107,149-155).
+ *   - RNG: counter-based Philox4x32-10, key = seed, counter = (global env id, episode, purpose|slot);
+ *     results depend only on (seed, env_id0 + i, episode[i]) -- never on launch geometry or sharding.
+ */
+#ifndef RENV_B200_H
+#define RENV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RENV_ABI_VERSION 1
+#define RENV_MAX_DIM 32          /* largest task_dim in the suite is 30 (jinja/random_humanoid.py) */
+#define RENV_NUM_STATS 6         /* episodes, sum R, sum R^2, min R, max R, sum length */
+
+enum renv_status {
+    RENV_OK = 0,
+    RENV_E_NULL = -1,            /* required pointer is NULL */
+    RENV_E_ALIGN = -2,           /* pointer or ld violates the alignment contract */
+    RENV_E_SIZE = -3,            /* n <= 0, ld < n, K <= 0 ... */
+    RENV_E_DIM = -4,             /* dim outside [1, RENV_MAX_DIM] (or != 4 for cartpole) */
+    RENV_E_DRTYPE = -5,          /* unknown dr_type (random_env.py:90 'Unknown dr_type') */
+    RENV_E_INTEGRATOR = -6,
+    RENV_E_ARG = -7
+};
+
+/* random_envs/random_env.py:72-90 -- the string keys of set_dr_distribution. */
+enum renv_dr_type {
+    RENV_DR_NONE = 0,            /* sampling is None / dr_training False: xi is left alone on reset */
+    RENV_DR_UNIFORM = 1,         /* random_env.py:150-151 */
+    RENV_DR_TRUNCNORM = 2,       /* random_env.py:153-171 */
+    RENV_DR_GAUSSIAN = 3         /* random_env.py:173-190 */
+};
+
+/* random_envs/random_cartpole.py:187-196: 'euler' vs anything else. */
+enum renv_integrator { RENV_EULER = 0, RENV_SEMI_IMPLICIT = 1 };
+
+/* Host-side image of RandomEnv's distribution state (random_env.py:102-121 de-interleaved):
+ *   uniform:            a = min_task,  b = max_task
+ *   truncnorm/gaussian: a = mean_task, b = stdev_task
+ *   lb[i] = get_task_lower_bound(i) (used by truncnorm only; gaussian's floor is the literal 0.1). */
+typedef struct renv_dr_cfg {
+    int32_t dr_type;
+    int32_t dim;
+    double a[RENV_MAX_DIM];
+    double b[RENV_MAX_DIM];
+    double lb[RENV_MAX_DIM];
+} renv_dr_cfg;
+
+/* One shard of cart-pole envs resident in HBM (device pointers, element type T = float | double). */
+typedef struct renv_cartpole_env {
+    void *state;                 /* T (4, ld)   RandomCartPoleEnv.state            :176,198 */
+    void *xi;                    /* T (4, ld)   gravity, cart_mass, pole_mass, pole_length :157-166 */
+    int32_t *elapsed;            /* (n) TimeLimit._elapsed_steps (gym 0.21)                 */
+    uint32_t *episode;           /* (n) Philox episode counter; bumped by every reset       */
+    int32_t *beyond;             /* (n) steps_beyond_done, -1 == None (:207-222); may be NULL when auto_reset */
+    int64_t n;                   /* envs in this shard */
+    int64_t ld;                  /* row stride of state/xi in elements, >= n */
+    uint64_t env_id0;            /* global id of env 0 of this shard (rank * n under contiguous sharding) */
+    uint64_t seed;               /* Philox key */
+} renv_cartpole_env;
+
+int renv_abi_version(void);
+const char *renv_strerror(int code);
+
+/* RandomEnv.sample_tasks(n) -> (n, dim) row-major  (random_env.py:145-203).
+ * Sample i uses Philox id = sample_id0 + i and episode field = call.  `violations` (may be NULL)
+ * counts gaussian dims whose three draws were all < 0.1 -- the host raises the reference's
+ * Exception('Not all samples were above > 0.1 after 2 attempts') when it is non-zero. */
+int renv_dr_sample_f32(float *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0,
+                       uint32_t call, unsigned long long *violations, void *stream);
+int renv_dr_sample_f64(double *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0,
+                       uint32_t call, unsigned long long *violations, void *stream);
+
+/* RandomCartPoleEnv.reset (random_cartpole.py:226-229) for every env with mask[i] != 0 (mask NULL = all),
+ * preceded by RandomEnv.set_random_task (random_env.py:37-39) when dr != NULL and dr->dr_type != NONE
+ * (the README.md:9 / MuJoCo-env behaviour; CartPole's own reset forgets it).  Also zeroes elapsed,
+ * sets beyond = -1 and bumps episode. */
+int renv_cartpole_reset_f32(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+                            unsigned long long *violations, void *stream);
+int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+                            unsigned long long *violations, void *stream);
+
+/* RandomCartPoleEnv.step (random_cartpole.py:172-224) for all n envs, fused with
+ *   TimeLimit.step (gym 0.21; max_steps <= 0 disables)  and
+ *   SyncVectorEnv auto-reset (gym 0.21; auto_reset != 0) incl. the DR resample above.
+ * action (n) in {0,1}; reward (n) T; done (n) u8; truncated (n) u8 or NULL.
+ * With auto_reset the state written back for a finished env is its reset state (the obs gym returns). */
+int renv_cartpole_step_f32(const renv_cartpole_env *env, const uint8_t *action, float *reward, uint8_t *done,
+                           uint8_t *truncated, int integrator, int max_steps, int auto_reset,
+                           const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
+int renv_cartpole_step_f64(const renv_cartpole_env *env, const uint8_t *action, double *reward, uint8_t *done,
+                           uint8_t *truncated, int integrator, int max_steps, int auto_reset,
+                           const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
+
+/* K fused steps with the linear policy a = [w.s + b > 0] evaluated in-kernel, auto-reset always on.
+ * State, xi and counters stay in registers for the K steps.  stats (device, RENV_NUM_STATS doubles,
+ * caller-initialised to {0,0,0,+inf,-inf,0}) is ACCUMULATED with the finished episodes' returns. */
+int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
+                              int max_steps, const renv_dr_cfg *dr, double *stats,
+                              unsigned long long *violations, void *stream);
+int renv_cartpole_rollout_f64(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
+                              int max_steps, const renv_dr_cfg *dr, double *stats,
+                              unsigned long long *violations, void *stream);
+
+/* action_space.sample() for n envs (test_random_policy.py:26): Bernoulli(1/2) bits of Philox block
+ * (env_id >> 7, step). */
+int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step,
+                           void *stream);
+
+/* Micro-benchmarks used by bench.py for the rollout's compute roofline: a dependent-FMA chain with
+ * `ilp` independent accumulators per thread; out (blocks*threads) keeps the result live.
+ * FLOPs = 2 * blocks * threads * ilp * iters. */
+int renv_fma_peak_f32(float *out, int blocks, int threads, int iters, void *stream);
+int renv_fma_peak_f64(double *out, int blocks, int threads, int iters, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RENV_B200_H */

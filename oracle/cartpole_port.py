@@ -92,7 +92,7 @@ class CartPolePort:
         return np.array(self.state)
 
     def step(self, action):
-        if not (isinstance(action, (int, np.integer)) and not isinstance(action, bool) and 0 <= int(action) < 2):
+        if not (isinstance(action, (int, np.integer)) and 0 <= int(action) < 2):
             raise AssertionError("%r (%s) invalid" % (action, type(action)))
         self.state, terminated = dynamics_step(self.state, self.xi, action,
                                                self.kinematics_integrator == "euler")

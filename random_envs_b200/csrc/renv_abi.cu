@@ -1,0 +1,241 @@
+// C ABI of librenv_b200.so (declared in include/renv.h): argument validation + kernel launches.
+// Stateless and re-entrant: nothing is allocated, cached or synchronised here.
+#include "../../include/renv.h"
+#include "renv_kernels.cuh"
+
+using namespace renv;
+
+namespace {
+
+inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+int to_cfg4(const renv_dr_cfg *dr, DrCfg4 *out)
+{
+    out->dr_type = kDrNone;
+    out->dim = 4;
+    for (int k = 0; k < 4; ++k) { out->a[k] = 0.0; out->b[k] = 0.0; out->lb[k] = 0.0; }
+    if (dr == nullptr || dr->dr_type == RENV_DR_NONE) return RENV_OK;
+    if (dr->dr_type < RENV_DR_NONE || dr->dr_type > RENV_DR_GAUSSIAN) return RENV_E_DRTYPE;
+    if (dr->dim != 4) return RENV_E_DIM;
+    out->dr_type = dr->dr_type;
+    for (int k = 0; k < 4; ++k) { out->a[k] = dr->a[k]; out->b[k] = dr->b[k]; out->lb[k] = dr->lb[k]; }
+    return RENV_OK;
+}
+
+template <typename T> int check_env(const renv_cartpole_env *env, bool need_beyond, EnvPtrs<T> *out)
+{
+    if (env == nullptr || env->state == nullptr || env->xi == nullptr || env->elapsed == nullptr ||
+        env->episode == nullptr)
+        return RENV_E_NULL;
+    if (need_beyond && env->beyond == nullptr) return RENV_E_NULL;
+    if (env->n <= 0 || env->ld < env->n) return RENV_E_SIZE;
+    constexpr int V = VecTraits<T>::V;
+    if (env->ld % V != 0) return RENV_E_ALIGN;
+    if (!aligned(env->state, 16) || !aligned(env->xi, 16) || !aligned(env->elapsed, 16) || !aligned(env->episode, 4) ||
+        (env->beyond && !aligned(env->beyond, 4)))
+        return RENV_E_ALIGN;
+    out->state = static_cast<T *>(env->state);
+    out->xi = static_cast<T *>(env->xi);
+    out->elapsed = env->elapsed;
+    out->episode = env->episode;
+    out->beyond = env->beyond;
+    out->n = env->n;
+    out->ld = env->ld;
+    out->env_id0 = env->env_id0;
+    out->seed = env->seed;
+    return RENV_OK;
+}
+
+inline int launch_status() { return (int)cudaGetLastError(); }
+
+template <typename T>
+int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0, uint32_t call,
+              unsigned long long *violations, void *stream)
+{
+    if (out == nullptr || cfg == nullptr) return RENV_E_NULL;
+    if (n <= 0) return RENV_E_SIZE;
+    if (cfg->dim < 1 || cfg->dim > RENV_MAX_DIM) return RENV_E_DIM;
+    if (cfg->dr_type < RENV_DR_UNIFORM || cfg->dr_type > RENV_DR_GAUSSIAN) return RENV_E_DRTYPE;
+    if (!aligned(out, 16)) return RENV_E_ALIGN;
+    DrCfgFull c;
+    c.dr_type = cfg->dr_type;
+    c.dim = cfg->dim;
+    for (int k = 0; k < 32; ++k) { c.a[k] = cfg->a[k]; c.b[k] = cfg->b[k]; c.lb[k] = cfg->lb[k]; }
+    const int64_t blocks = (n + kTileSamples - 1) / kTileSamples;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    const size_t smem = (size_t)kTileSamples * cfg->dim * sizeof(T);
+    dr_sample_kernel<T><<<(unsigned)blocks, kSampleThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        out, n, c, seed, sample_id0, call, violations);
+    return launch_status();
+}
+
+template <typename T>
+int cartpole_reset(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+                   unsigned long long *violations, void *stream)
+{
+    ResetArgs<T> a;
+    int rc = check_env<T>(env, false, &a.env);
+    if (rc) return rc;
+    rc = to_cfg4(dr, &a.dr);
+    if (rc) return rc;
+    a.mask = mask;
+    a.violations = violations;
+    const int64_t blocks = (env->n + 255) / 256;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    cartpole_reset_kernel<T><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_status();
+}
+
+template <typename T>
+int cartpole_step(const renv_cartpole_env *env, const uint8_t *action, T *reward, uint8_t *done, uint8_t *truncated,
+                  int integrator, int max_steps, int auto_reset, const renv_dr_cfg *dr,
+                  unsigned long long *violations, void *stream)
+{
+    StepArgs<T> a;
+    int rc = check_env<T>(env, !auto_reset, &a.env);
+    if (rc) return rc;
+    if (action == nullptr || reward == nullptr || done == nullptr) return RENV_E_NULL;
+    if (!aligned(action, 4) || !aligned(reward, 16) || !aligned(done, 4) || (truncated && !aligned(truncated, 4)))
+        return RENV_E_ALIGN;
+    if (integrator != RENV_EULER && integrator != RENV_SEMI_IMPLICIT) return RENV_E_INTEGRATOR;
+    rc = to_cfg4(auto_reset ? dr : nullptr, &a.dr);
+    if (rc) return rc;
+    a.action = action; a.reward = reward; a.done = done; a.truncated = truncated;
+    a.euler = integrator == RENV_EULER;
+    a.max_steps = max_steps;
+    a.auto_reset = auto_reset != 0;
+    a.violations = violations;
+    constexpr int V = VecTraits<T>::V;
+    const int64_t groups = (env->n + V - 1) / V;
+    const int64_t blocks = (groups + 255) / 256;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    cartpole_step_kernel<T><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_status();
+}
+
+template <typename T>
+int cartpole_rollout(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator, int max_steps,
+                     const renv_dr_cfg *dr, double *stats, unsigned long long *violations, void *stream)
+{
+    RolloutArgs<T> a;
+    int rc = check_env<T>(env, false, &a.env);
+    if (rc) return rc;
+    if (w == nullptr || stats == nullptr) return RENV_E_NULL;
+    if (!aligned(stats, 8)) return RENV_E_ALIGN;
+    if (K <= 0) return RENV_E_SIZE;
+    if (integrator != RENV_EULER && integrator != RENV_SEMI_IMPLICIT) return RENV_E_INTEGRATOR;
+    rc = to_cfg4(dr, &a.dr);
+    if (rc) return rc;
+    a.policy = Policy<T>{ (T)w[0], (T)w[1], (T)w[2], (T)w[3], (T)b };
+    a.K = K;
+    a.euler = integrator == RENV_EULER;
+    a.max_steps = max_steps;
+    a.stats = stats;
+    a.violations = violations;
+    const int64_t blocks = (env->n + kRolloutThreads - 1) / kRolloutThreads;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    cartpole_rollout_kernel<T><<<(unsigned)blocks, kRolloutThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return launch_status();
+}
+
+template <typename T> int fma_peak(T *out, int blocks, int threads, int iters, void *stream)
+{
+    if (out == nullptr) return RENV_E_NULL;
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0) return RENV_E_SIZE;
+    fma_peak_kernel<T><<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(out, iters);
+    return launch_status();
+}
+
+}  // namespace
+
+extern "C" {
+
+int renv_abi_version(void) { return RENV_ABI_VERSION; }
+
+const char *renv_strerror(int code)
+{
+    switch (code) {
+    case RENV_OK: return "ok";
+    case RENV_E_NULL: return "required pointer is NULL";
+    case RENV_E_ALIGN: return "pointer or ld violates the alignment contract (16 B data, 4 B byte arrays, ld % V)";
+    case RENV_E_SIZE: return "invalid size (n <= 0, ld < n, K <= 0 or grid too large)";
+    case RENV_E_DIM: return "dim outside [1, 32] (cart-pole needs 4)";
+    case RENV_E_DRTYPE: return "Unknown dr_type";
+    case RENV_E_INTEGRATOR: return "unknown integrator";
+    case RENV_E_ARG: return "invalid argument";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown renv status";
+    }
+}
+
+int renv_dr_sample_f32(float *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0, uint32_t call,
+                       unsigned long long *violations, void *stream)
+{
+    return dr_sample<float>(out, n, cfg, seed, sample_id0, call, violations, stream);
+}
+int renv_dr_sample_f64(double *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0,
+                       uint32_t call, unsigned long long *violations, void *stream)
+{
+    return dr_sample<double>(out, n, cfg, seed, sample_id0, call, violations, stream);
+}
+
+int renv_cartpole_reset_f32(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+                            unsigned long long *violations, void *stream)
+{
+    return cartpole_reset<float>(env, mask, dr, violations, stream);
+}
+int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+                            unsigned long long *violations, void *stream)
+{
+    return cartpole_reset<double>(env, mask, dr, violations, stream);
+}
+
+int renv_cartpole_step_f32(const renv_cartpole_env *env, const uint8_t *action, float *reward, uint8_t *done,
+                           uint8_t *truncated, int integrator, int max_steps, int auto_reset, const renv_dr_cfg *dr,
+                           unsigned long long *violations, void *stream)
+{
+    return cartpole_step<float>(env, action, reward, done, truncated, integrator, max_steps, auto_reset, dr,
+                                violations, stream);
+}
+int renv_cartpole_step_f64(const renv_cartpole_env *env, const uint8_t *action, double *reward, uint8_t *done,
+                           uint8_t *truncated, int integrator, int max_steps, int auto_reset, const renv_dr_cfg *dr,
+                           unsigned long long *violations, void *stream)
+{
+    return cartpole_step<double>(env, action, reward, done, truncated, integrator, max_steps, auto_reset, dr,
+                                 violations, stream);
+}
+
+int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
+                              int max_steps, const renv_dr_cfg *dr, double *stats, unsigned long long *violations,
+                              void *stream)
+{
+    return cartpole_rollout<float>(env, w, b, K, integrator, max_steps, dr, stats, violations, stream);
+}
+int renv_cartpole_rollout_f64(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
+                              int max_steps, const renv_dr_cfg *dr, double *stats, unsigned long long *violations,
+                              void *stream)
+{
+    return cartpole_rollout<double>(env, w, b, K, integrator, max_steps, dr, stats, violations, stream);
+}
+
+int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step, void *stream)
+{
+    if (action == nullptr) return RENV_E_NULL;
+    if (n <= 0) return RENV_E_SIZE;
+    if (!aligned(action, 16)) return RENV_E_ALIGN;
+    const int64_t threads = (n + 15) / 16;
+    const int64_t blocks = (threads + 255) / 256;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    random_actions_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(action, n, env_id0, seed, step);
+    return launch_status();
+}
+
+int renv_fma_peak_f32(float *out, int blocks, int threads, int iters, void *stream)
+{
+    return fma_peak<float>(out, blocks, threads, iters, stream);
+}
+int renv_fma_peak_f64(double *out, int blocks, int threads, int iters, void *stream)
+{
+    return fma_peak<double>(out, blocks, threads, iters, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// Cart-pole dynamics, termination, reward and reset as device functions shared by the single-step
+// and the fused-rollout kernels (so both produce bit-identical trajectories).
+//
+// Reference: random_envs/random_cartpole.py
+//   constants :74-86, dynamics :176-185, integrators :187-196, termination :200-205,
+//   reward / steps_beyond_done :207-222, reset :226-229, set_task :157-166.
+//
+// Two arithmetic contracts, one per element type:
+//   double  the PARITY path.  Every operation is an explicitly rounded __d*_rn intrinsic in the
+//           reference's operator order, so nvcc can neither contract to FMA nor reassociate; the only
+//           difference from CPython is sin/cos (CUDA <= 2 ulp vs glibc) and pow(x,2) vs x*x.
+//   float   the THROUGHPUT path.  Same formulae with hand-placed FMAs and 1/total_mass hoisted;
+//           written with intrinsics as well so the result does not depend on which kernel inlines it.
+#pragma once
+#include "renv_dr.cuh"
+
+namespace renv {
+
+// random_cartpole.py:74-86
+constexpr double kForceMag = 10.0;
+constexpr double kPolemassLength = 0.05;   // pole_mass*pole_length frozen at construction; set_task never refreshes it
+constexpr double kTau = 0.02;
+constexpr double kXThreshold = 2.4;
+constexpr double kThetaThreshold = 0.20943951023931953;   // 12 * 2 * math.pi / 360
+constexpr double kFourThirds = 4.0 / 3.0;
+
+template <typename T> struct Xi { T gravity, cart_mass, pole_mass, pole_length; };
+template <typename T> struct State { T x, x_dot, theta, theta_dot; };
+
+// Loop-invariant (per episode) quantities of the float path.
+template <typename T> struct Derived;
+template <> struct Derived<double> { };
+template <> struct Derived<float> { float inv_total_mass, pm_over_total, pml_over_total; };
+
+__device__ __forceinline__ Derived<double> derive(const Xi<double> &) { return {}; }
+__device__ __forceinline__ Derived<float> derive(const Xi<float> &p)
+{
+    Derived<float> d;
+    d.inv_total_mass = __frcp_rn(__fadd_rn(p.pole_mass, p.cart_mass));
+    d.pm_over_total = __fmul_rn(p.pole_mass, d.inv_total_mass);
+    d.pml_over_total = __fmul_rn((float)kPolemassLength, d.inv_total_mass);
+    return d;
+}
+
+// ---- dynamics: returns terminated -----------------------------------------------------------------
+__device__ __forceinline__ bool dynamics(State<double> &s, const Xi<double> &p, const Derived<double> &, int action,
+                                         bool euler)
+{
+    const double total_mass = __dadd_rn(p.pole_mass, p.cart_mass);                       // :166
+    const double force = action == 1 ? kForceMag : -kForceMag;                           // :177
+    double sn, cs;
+    sincos(s.theta, &sn, &cs);                                                           // :178-179
+    // temp = (force + polemass_length * theta_dot**2 * sintheta) / total_mass            :183
+    const double temp = __ddiv_rn(
+        __dadd_rn(force, __dmul_rn(__dmul_rn(kPolemassLength, __dmul_rn(s.theta_dot, s.theta_dot)), sn)), total_mass);
+    // thetaacc = (g*sin - cos*temp) / (l * (4/3 - m_p*cos**2/total_mass))                :184
+    const double num = __dsub_rn(__dmul_rn(p.gravity, sn), __dmul_rn(cs, temp));
+    const double den = __dmul_rn(
+        p.pole_length, __dsub_rn(kFourThirds, __ddiv_rn(__dmul_rn(p.pole_mass, __dmul_rn(cs, cs)), total_mass)));
+    const double theta_acc = __ddiv_rn(num, den);
+    // xacc = temp - polemass_length * thetaacc * costheta / total_mass                   :185
+    const double x_acc =
+        __dsub_rn(temp, __ddiv_rn(__dmul_rn(__dmul_rn(kPolemassLength, theta_acc), cs), total_mass));
+    if (euler) {                                                                         // :187-191
+        s.x = __dadd_rn(s.x, __dmul_rn(kTau, s.x_dot));
+        s.x_dot = __dadd_rn(s.x_dot, __dmul_rn(kTau, x_acc));
+        s.theta = __dadd_rn(s.theta, __dmul_rn(kTau, s.theta_dot));
+        s.theta_dot = __dadd_rn(s.theta_dot, __dmul_rn(kTau, theta_acc));
+    } else {                                                                             // :192-196
+        s.x_dot = __dadd_rn(s.x_dot, __dmul_rn(kTau, x_acc));
+        s.x = __dadd_rn(s.x, __dmul_rn(kTau, s.x_dot));
+        s.theta_dot = __dadd_rn(s.theta_dot, __dmul_rn(kTau, theta_acc));
+        s.theta = __dadd_rn(s.theta, __dmul_rn(kTau, s.theta_dot));
+    }
+    return s.x < -kXThreshold || s.x > kXThreshold || s.theta < -kThetaThreshold || s.theta > kThetaThreshold;  // :200-205
+}
+
+__device__ __forceinline__ bool dynamics(State<float> &s, const Xi<float> &p, const Derived<float> &d, int action,
+                                         bool euler)
+{
+    const float force = action == 1 ? (float)kForceMag : -(float)kForceMag;
+    float sn, cs;
+    sincosf(s.theta, &sn, &cs);
+    const float temp = __fmul_rn(fmaf(__fmul_rn(s.theta_dot, s.theta_dot), __fmul_rn((float)kPolemassLength, sn), force),
+                                 d.inv_total_mass);
+    const float num = fmaf(p.gravity, sn, -__fmul_rn(cs, temp));
+    const float den = __fmul_rn(p.pole_length, fmaf(-d.pm_over_total, __fmul_rn(cs, cs), (float)kFourThirds));
+    const float theta_acc = __fdiv_rn(num, den);
+    const float x_acc = fmaf(-__fmul_rn(d.pml_over_total, cs), theta_acc, temp);
+    const float tau = (float)kTau;
+    if (euler) {
+        s.x = fmaf(tau, s.x_dot, s.x);
+        s.x_dot = fmaf(tau, x_acc, s.x_dot);
+        s.theta = fmaf(tau, s.theta_dot, s.theta);
+        s.theta_dot = fmaf(tau, theta_acc, s.theta_dot);
+    } else {
+        s.x_dot = fmaf(tau, x_acc, s.x_dot);
+        s.x = fmaf(tau, s.x_dot, s.x);
+        s.theta_dot = fmaf(tau, theta_acc, s.theta_dot);
+        s.theta = fmaf(tau, s.theta_dot, s.theta);
+    }
+    return s.x < -(float)kXThreshold || s.x > (float)kXThreshold || s.theta < -(float)kThetaThreshold ||
+           s.theta > (float)kThetaThreshold;
+}
+
+// ---- linear policy a = [w.s + b > 0] -----------------------------------------------------------
+template <typename T> struct Policy { T w0, w1, w2, w3, b; };
+
+__device__ __forceinline__ int policy_action(const Policy<double> &q, const State<double> &s)
+{
+    double acc = __dmul_rn(q.w0, s.x);                      // left-to-right, separately rounded
+    acc = __dadd_rn(acc, __dmul_rn(q.w1, s.x_dot));
+    acc = __dadd_rn(acc, __dmul_rn(q.w2, s.theta));
+    acc = __dadd_rn(acc, __dmul_rn(q.w3, s.theta_dot));
+    acc = __dadd_rn(acc, q.b);
+    return acc > 0.0;
+}
+__device__ __forceinline__ int policy_action(const Policy<float> &q, const State<float> &s)
+{
+    float acc = __fmul_rn(q.w0, s.x);
+    acc = fmaf(q.w1, s.x_dot, acc);
+    acc = fmaf(q.w2, s.theta, acc);
+    acc = fmaf(q.w3, s.theta_dot, acc);
+    return __fadd_rn(acc, q.b) > 0.0f;
+}
+
+// ---- reset: s0 ~ U(-0.05, 0.05)^4 (:227) and, when DR is on, xi ~ sample_task() ---------------------
+__device__ __forceinline__ void init_state(State<float> &s, uint64_t seed, uint64_t id, uint32_t episode)
+{
+    float u[4];
+    Pack<float>::uniforms(draw_block(seed, id, episode, kInit, 0), u);
+    s.x = fmaf(0.1f, u[0], -0.05f);
+    s.x_dot = fmaf(0.1f, u[1], -0.05f);
+    s.theta = fmaf(0.1f, u[2], -0.05f);
+    s.theta_dot = fmaf(0.1f, u[3], -0.05f);
+}
+__device__ __forceinline__ void init_state(State<double> &s, uint64_t seed, uint64_t id, uint32_t episode)
+{
+    double u[2], v[2];
+    Pack<double>::uniforms(draw_block(seed, id, episode, kInit, 0), u);
+    Pack<double>::uniforms(draw_block(seed, id, episode, kInit, 1), v);
+    s.x = __dadd_rn(-0.05, __dmul_rn(0.1, u[0]));           // numpy: low + (high - low) * u
+    s.x_dot = __dadd_rn(-0.05, __dmul_rn(0.1, u[1]));
+    s.theta = __dadd_rn(-0.05, __dmul_rn(0.1, v[0]));
+    s.theta_dot = __dadd_rn(-0.05, __dmul_rn(0.1, v[1]));
+}
+
+template <typename T>
+__device__ __forceinline__ unsigned sample_xi(Xi<T> &p, const DrCfg4 &cfg, uint64_t seed, uint64_t id, uint32_t episode)
+{
+    constexpr int P = Pack<T>::kPerBlock;
+    T v[4] = { p.gravity, p.cart_mass, p.pole_mass, p.pole_length };
+    unsigned violations = 0;
+#pragma unroll
+    for (int j = 0; j < 4 / P; ++j) violations += sample_dim_block<T>(cfg, seed, id, episode, kXi, j, v + j * P);
+    p.gravity = v[0]; p.cart_mass = v[1]; p.pole_mass = v[2]; p.pole_length = v[3];
+    return violations;
+}
+
+}  // namespace renv

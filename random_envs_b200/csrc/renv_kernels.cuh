@@ -1,0 +1,419 @@
+// sm_100a kernels of the DR cart-pole hot path.  Launched only through the C ABI in renv_abi.cu.
+//
+// Memory design (HBM3e-bound single step): structure-of-arrays, one thread owns V consecutive envs
+// (V = 4 floats / 2 doubles = one 128-bit access per row), so every global access of the main path is
+// a fully coalesced LDG.E.128 / STG.E.128: per env-step 37 B read + 25 B written in fp32 (62 B),
+// 69 + 45 = 114 B in fp64 (DESIGN.md "algorithmic bytes").  All loads are issued before the first
+// use (10 independent 128-bit requests per thread in flight).  Auto-reset and the DR resample are
+// fused into the same kernel: only envs that finished touch `episode` and rewrite `xi`.
+#pragma once
+#include <cuda_runtime.h>
+#include "renv_cartpole.cuh"
+
+namespace renv {
+
+template <typename T> struct VecTraits;
+template <> struct VecTraits<float> {
+    static constexpr int V = 4;
+    using Real = float4; using Int = int4; using Byte = uchar4;
+};
+template <> struct VecTraits<double> {
+    static constexpr int V = 2;
+    using Real = double2; using Int = int2; using Byte = uchar2;
+};
+
+template <typename Vec, typename S, int V> __device__ __forceinline__ void vload(S (&dst)[V], const S *src)
+{
+    static_assert(sizeof(Vec) == sizeof(S) * V, "vector width");
+    const Vec v = *reinterpret_cast<const Vec *>(src);
+    const S *e = reinterpret_cast<const S *>(&v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) dst[k] = e[k];
+}
+template <typename Vec, typename S, int V> __device__ __forceinline__ void vstore(S *dst, const S (&src)[V])
+{
+    Vec v;
+    S *e = reinterpret_cast<S *>(&v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) e[k] = src[k];
+    *reinterpret_cast<Vec *>(dst) = v;
+}
+
+template <typename T> struct EnvPtrs {
+    T *state; T *xi; int32_t *elapsed; uint32_t *episode; int32_t *beyond;
+    int64_t n, ld; uint64_t env_id0, seed;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Single step: RandomCartPoleEnv.step + TimeLimit.step + SyncVectorEnv auto-reset (+ set_random_task)
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct StepArgs {
+    EnvPtrs<T> env;
+    const uint8_t *action; T *reward; uint8_t *done; uint8_t *truncated;
+    int euler, max_steps, auto_reset;
+    DrCfg4 dr;
+    unsigned long long *violations;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) cartpole_step_kernel(const StepArgs<T> a)
+{
+    using VT = VecTraits<T>;
+    constexpr int V = VT::V;
+    const int64_t group = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = group * V;
+    const int64_t n = a.env.n, ld = a.env.ld;
+    if (i0 >= n) return;
+    const bool full = i0 + V <= n;
+
+    T s[4][V], p[4][V];
+    int32_t el[V];
+    uint8_t act[V];
+    if (full) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vload<typename VT::Real>(s[c], a.env.state + c * ld + i0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vload<typename VT::Real>(p[c], a.env.xi + c * ld + i0);
+        vload<typename VT::Int>(el, a.env.elapsed + i0);
+        vload<typename VT::Byte>(act, a.action + i0);
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const bool ok = i0 + v < n;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s[c][v] = ok ? a.env.state[c * ld + i0 + v] : T(0);
+                p[c][v] = ok ? a.env.xi[c * ld + i0 + v] : T(1);
+            }
+            el[v] = ok ? a.env.elapsed[i0 + v] : 0;
+            act[v] = ok ? a.action[i0 + v] : 0;
+        }
+    }
+
+    T rew[V];
+    uint8_t dn[V], tr[V];
+    unsigned finished = 0;
+    const bool euler = a.euler != 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        State<T> st = { s[0][v], s[1][v], s[2][v], s[3][v] };
+        const Xi<T> xi = { p[0][v], p[1][v], p[2][v], p[3][v] };
+        const bool terminated = dynamics(st, xi, derive(xi), act[v], euler);
+        s[0][v] = st.x; s[1][v] = st.x_dot; s[2][v] = st.theta; s[3][v] = st.theta_dot;
+        el[v] += 1;                                                    // TimeLimit.step
+        bool done = terminated, trunc = false;
+        if (a.max_steps > 0 && el[v] >= a.max_steps) { trunc = !terminated; done = true; }
+        T r = T(1);                                                    // :207-212
+        if (!a.auto_reset && a.env.beyond != nullptr && i0 + v < n && terminated) {
+            const int32_t b = a.env.beyond[i0 + v];                    // :213-222 (only reachable without auto-reset)
+            a.env.beyond[i0 + v] = b < 0 ? 0 : b + 1;
+            r = b < 0 ? T(1) : T(0);
+        }
+        rew[v] = r; dn[v] = done; tr[v] = trunc;
+        if (done && a.auto_reset && i0 + v < n) finished |= 1u << v;
+    }
+
+    // SyncVectorEnv auto-reset (+ set_random_task when DR is on).  Executed max-over-lanes(popc) times per
+    // warp, not V times; no dynamically indexed register arrays (selects only).
+    unsigned viol = 0;
+    while (finished) {
+        const int v = __ffs(finished) - 1;
+        finished &= finished - 1;
+        const int64_t i = i0 + v;
+        const uint64_t id = a.env.env_id0 + (uint64_t)i;
+        const uint32_t ep = a.env.episode[i] + 1u;
+        a.env.episode[i] = ep;
+        State<T> st;
+        init_state(st, a.env.seed, id, ep);
+        Xi<T> xi;
+        const bool resample = a.dr.dr_type != kDrNone;
+        if (resample) {
+            xi = Xi<T>{ T(0), T(0), T(0), T(0) };
+            viol += sample_xi(xi, a.dr, a.env.seed, id, ep);
+            a.env.xi[0 * ld + i] = xi.gravity; a.env.xi[1 * ld + i] = xi.cart_mass;
+            a.env.xi[2 * ld + i] = xi.pole_mass; a.env.xi[3 * ld + i] = xi.pole_length;
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (k == v) { s[0][k] = st.x; s[1][k] = st.x_dot; s[2][k] = st.theta; s[3][k] = st.theta_dot; el[k] = 0; }
+        }
+    }
+    if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
+
+    if (full) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vstore<typename VT::Real>(a.env.state + c * ld + i0, s[c]);
+        vstore<typename VT::Int>(a.env.elapsed + i0, el);
+        vstore<typename VT::Real>(a.reward + i0, rew);
+        vstore<typename VT::Byte>(a.done + i0, dn);
+        if (a.truncated) vstore<typename VT::Byte>(a.truncated + i0, tr);
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (i0 + v < n) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) a.env.state[c * ld + i0 + v] = s[c][v];
+                a.env.elapsed[i0 + v] = el[v];
+                a.reward[i0 + v] = rew[v];
+                a.done[i0 + v] = dn[v];
+                if (a.truncated) a.truncated[i0 + v] = tr[v];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reset: RandomCartPoleEnv.reset (+ set_random_task) for masked envs
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct ResetArgs {
+    EnvPtrs<T> env;
+    const uint8_t *mask;
+    DrCfg4 dr;
+    unsigned long long *violations;
+};
+
+template <typename T> __global__ void __launch_bounds__(256) cartpole_reset_kernel(const ResetArgs<T> a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.env.n) return;
+    if (a.mask && !a.mask[i]) return;
+    const int64_t ld = a.env.ld;
+    const uint64_t id = a.env.env_id0 + (uint64_t)i;
+    const uint32_t ep = a.env.episode[i] + 1u;
+    a.env.episode[i] = ep;
+    a.env.elapsed[i] = 0;
+    if (a.env.beyond) a.env.beyond[i] = -1;
+    State<T> st;
+    init_state(st, a.env.seed, id, ep);
+    a.env.state[0 * ld + i] = st.x; a.env.state[1 * ld + i] = st.x_dot;
+    a.env.state[2 * ld + i] = st.theta; a.env.state[3 * ld + i] = st.theta_dot;
+    if (a.dr.dr_type != kDrNone) {
+        Xi<T> xi = { T(0), T(0), T(0), T(0) };
+        const unsigned viol = sample_xi(xi, a.dr, a.env.seed, id, ep);
+        a.env.xi[0 * ld + i] = xi.gravity; a.env.xi[1 * ld + i] = xi.cart_mass;
+        a.env.xi[2 * ld + i] = xi.pole_mass; a.env.xi[3 * ld + i] = xi.pole_length;
+        if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused K-step rollout with in-register state/xi/counters and an in-kernel linear policy
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_f64(double *addr, double v)
+{
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *p;
+    while (v < __longlong_as_double((long long)old)) {
+        const unsigned long long seen = atomicCAS(p, old, (unsigned long long)__double_as_longlong(v));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+__device__ __forceinline__ void atomic_max_f64(double *addr, double v)
+{
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *p;
+    while (v > __longlong_as_double((long long)old)) {
+        const unsigned long long seen = atomicCAS(p, old, (unsigned long long)__double_as_longlong(v));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+
+template <typename T> struct RolloutArgs {
+    EnvPtrs<T> env;
+    Policy<T> policy;
+    int K, euler, max_steps;
+    DrCfg4 dr;
+    double *stats;
+    unsigned long long *violations;
+};
+
+constexpr int kRolloutThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kRolloutThreads) cartpole_rollout_kernel(const RolloutArgs<T> a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ld = a.env.ld;
+    const bool live = i < a.env.n;
+
+    // per-thread episode statistics (return == length here: reward is 1.0 on every step, :207-212)
+    double sum_r = 0.0, sum_r2 = 0.0;
+    float min_r = __int_as_float(0x7f800000), max_r = __int_as_float(0xff800000);
+    unsigned episodes = 0, sum_len = 0, viol = 0;
+
+    if (live) {
+        State<T> s = { a.env.state[i], a.env.state[ld + i], a.env.state[2 * ld + i], a.env.state[3 * ld + i] };
+        Xi<T> p = { a.env.xi[i], a.env.xi[ld + i], a.env.xi[2 * ld + i], a.env.xi[3 * ld + i] };
+        Derived<T> d = derive(p);
+        int32_t el = a.env.elapsed[i];
+        uint32_t ep = a.env.episode[i];
+        const uint64_t id = a.env.env_id0 + (uint64_t)i;
+        const bool euler = a.euler != 0;
+        const bool resample = a.dr.dr_type != kDrNone;
+        bool xi_dirty = false;
+        for (int k = 0; k < a.K; ++k) {
+            const int action = policy_action(a.policy, s);
+            const bool terminated = dynamics(s, p, d, action, euler);
+            el += 1;
+            if (terminated || (a.max_steps > 0 && el >= a.max_steps)) {
+                const float ret = (float)el;
+                episodes += 1; sum_len += (unsigned)el;
+                sum_r += (double)ret; sum_r2 += (double)ret * (double)ret;
+                min_r = fminf(min_r, ret); max_r = fmaxf(max_r, ret);
+                ep += 1; el = 0;
+                if (resample) {
+                    p = Xi<T>{ T(0), T(0), T(0), T(0) };
+                    viol += sample_xi(p, a.dr, a.env.seed, id, ep);
+                    d = derive(p);
+                    xi_dirty = true;
+                }
+                init_state(s, a.env.seed, id, ep);
+            }
+        }
+        a.env.state[i] = s.x; a.env.state[ld + i] = s.x_dot; a.env.state[2 * ld + i] = s.theta;
+        a.env.state[3 * ld + i] = s.theta_dot;
+        if (xi_dirty) {
+            a.env.xi[i] = p.gravity; a.env.xi[ld + i] = p.cart_mass; a.env.xi[2 * ld + i] = p.pole_mass;
+            a.env.xi[3 * ld + i] = p.pole_length;
+        }
+        a.env.elapsed[i] = el;
+        a.env.episode[i] = ep;
+    }
+
+    // warp shuffle -> shared -> one set of atomics per CTA
+    double cnt = (double)episodes, len = (double)sum_len;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        len += __shfl_xor_sync(0xffffffffu, len, off);
+        sum_r += __shfl_xor_sync(0xffffffffu, sum_r, off);
+        sum_r2 += __shfl_xor_sync(0xffffffffu, sum_r2, off);
+        min_r = fminf(min_r, __shfl_xor_sync(0xffffffffu, min_r, off));
+        max_r = fmaxf(max_r, __shfl_xor_sync(0xffffffffu, max_r, off));
+        viol += __shfl_xor_sync(0xffffffffu, viol, off);
+    }
+    __shared__ double sh[kRolloutThreads / 32][4];
+    __shared__ float shm[kRolloutThreads / 32][2];
+    __shared__ unsigned shv[kRolloutThreads / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh[warp][0] = cnt; sh[warp][1] = sum_r; sh[warp][2] = sum_r2; sh[warp][3] = len;
+        shm[warp][0] = min_r; shm[warp][1] = max_r; shv[warp] = viol;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 1; w < nw; ++w) {
+            cnt += sh[w][0]; sum_r += sh[w][1]; sum_r2 += sh[w][2]; len += sh[w][3];
+            min_r = fminf(min_r, shm[w][0]); max_r = fmaxf(max_r, shm[w][1]); viol += shv[w];
+        }
+        if (cnt > 0.0) {
+            atomicAdd(a.stats + 0, cnt);
+            atomicAdd(a.stats + 1, sum_r);
+            atomicAdd(a.stats + 2, sum_r2);
+            atomic_min_f64(a.stats + 3, (double)min_r);
+            atomic_max_f64(a.stats + 4, (double)max_r);
+            atomicAdd(a.stats + 5, len);
+        }
+        if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RandomEnv.sample_tasks(n) -> (n, dim) row-major, dim <= 32
+// ------------------------------------------------------------------------------------------------
+// A CTA produces kTileSamples consecutive samples.  Work item = (sample, dim block of 4 floats / 2
+// doubles = one Philox call); values go to a shared-memory tile that is contiguous in the output, so
+// the tile is written back with fully coalesced 128-bit stores whatever `dim` is (30 is not a
+// multiple of 4: a thread-per-sample store would touch 32 sectors per instruction).
+constexpr int kTileSamples = 128;
+constexpr int kSampleThreads = 256;
+
+struct DrCfgFull { int dr_type; int dim; double a[32]; double b[32]; double lb[32]; };
+
+template <typename T>
+__global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict__ out, int64_t n, const DrCfgFull cfg,
+                                                                   uint64_t seed, uint64_t sample_id0, uint32_t call,
+                                                                   unsigned long long *violations)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *tile = reinterpret_cast<T *>(smem_raw);
+    constexpr int P = Pack<T>::kPerBlock;
+    const int dim = cfg.dim;
+    const int blocks_per_sample = (dim + P - 1) / P;
+    const int64_t first = (int64_t)blockIdx.x * kTileSamples;
+    const int samples = (int)min((int64_t)kTileSamples, n - first);
+    const int items = samples * blocks_per_sample;
+    unsigned viol = 0;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int sidx = it / blocks_per_sample, j = it - sidx * blocks_per_sample;
+        T v[P];
+        viol += sample_dim_block<T>(cfg, seed, sample_id0 + (uint64_t)(first + sidx), call, kTasks, j, v);
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+            if (j * P + k < dim) tile[sidx * dim + j * P + k] = v[k];
+    }
+    if (viol && violations) atomicAdd(violations, (unsigned long long)viol);
+    __syncthreads();
+    const int total = samples * dim;
+    T *dst = out + first * dim;
+    constexpr int W = 16 / sizeof(T);
+    const int nvec = total / W;
+    for (int q = threadIdx.x; q < nvec; q += blockDim.x)
+        reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(tile)[q];
+    for (int q = nvec * W + threadIdx.x; q < total; q += blockDim.x) dst[q] = tile[q];
+}
+
+// ------------------------------------------------------------------------------------------------
+// action_space.sample() for every env: Bernoulli(1/2) bits
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) random_actions_kernel(uint8_t *__restrict__ action, int64_t n, uint64_t env_id0,
+                                                             uint64_t seed, uint32_t step)
+{
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    uint64_t cached_group = ~0ull;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    uint32_t words[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint64_t e = env_id0 + (uint64_t)(i0 + k);
+        if ((e >> 7) != cached_group) {
+            cached_group = e >> 7;
+            r = draw_block(seed, cached_group, step, kAction, 0);
+        }
+        const uint32_t sel = (uint32_t)(e >> 5) & 3u;
+        const uint32_t word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+        const uint32_t bit = (word >> (e & 31)) & 1u;
+        words[k >> 2] |= bit << (8 * (k & 3));
+    }
+    if (i0 + 16 <= n) {
+        *reinterpret_cast<uint4 *>(action + i0) = make_uint4(words[0], words[1], words[2], words[3]);
+    } else {
+        for (int k = 0; k < 16 && i0 + k < n; ++k) action[i0 + k] = (uint8_t)((words[k >> 2] >> (8 * (k & 3))) & 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FMA-throughput micro-benchmark (roofline denominator of the fused rollout)
+// ------------------------------------------------------------------------------------------------
+constexpr int kFmaIlp = 8;
+template <typename T> __global__ void fma_peak_kernel(T *out, int iters)
+{
+    T acc[kFmaIlp];
+    const T a = (T)1.0000001, b = (T)1e-7;
+#pragma unroll
+    for (int k = 0; k < kFmaIlp; ++k) acc[k] = (T)(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < kFmaIlp; ++k) acc[k] = acc[k] * a + b;
+    }
+    T sum = 0;
+#pragma unroll
+    for (int k = 0; k < kFmaIlp; ++k) sum += acc[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+}  // namespace renv

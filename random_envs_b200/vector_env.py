@@ -1,0 +1,345 @@
+"""Vectorised, tensor-in/tensor-out RandomCartPole: N envs resident in HBM, one kernel per call.
+
+Same method names as the reference's single env (random_cartpole.py / random_env.py): ``reset``,
+``step``, ``seed``, ``get_task``, ``set_task``, ``set_random_task``, ``set_dr_distribution``,
+``set_dr_training`` ...; arguments and results are batched torch CUDA tensors:
+
+    reset()        -> obs (N, 4)
+    step(actions)  -> obs (N, 4), reward (N,), done (N,) bool, info {'TimeLimit.truncated': (N,) bool}
+    get_task()     -> (N, 4)            set_task(Tensor(N, 4) | g, m_c, m_p, l)
+    rollout(w, b, K) -> None            (K fused steps of the linear policy a = [w.s + b > 0])
+    episode_stats()  -> dict            (returns of the episodes finished inside rollouts)
+
+``step`` fuses what the reference stack does in three Python layers: ``RandomCartPoleEnv.step``
+(random_cartpole.py:172-224), gym 0.21 ``TimeLimit.step`` (max_episode_steps=500, :294) and gym 0.21
+``SyncVectorEnv`` auto-reset, including the DR resample on reset when ``dr_training`` is on
+(README.md:9; random_env.py:37-39).  The returned tensors are views of the env's own buffers (the
+reference's ``obs`` likewise aliases ``state``): they are overwritten by the next call.
+
+Storage is structure-of-arrays ``(4, ld)`` so that the kernels read and write 128-bit coalesced
+vectors; ``obs``/``get_task`` expose the transposed ``(N, 4)`` view.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _device, _lib
+from .random_env import RandomEnv
+from .xi_tables import get_table
+
+_TABLE = get_table("RandomCartPole-v0")
+NOMINAL_TASK = (9.8, 1.0, 0.1, 0.5)                 # random_cartpole.py:74-78
+THETA_THRESHOLD_RADIANS = 12 * 2 * math.pi / 360   # :85
+X_THRESHOLD = 2.4                                  # :86
+MAX_EPISODE_STEPS = 500                            # :294
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class RandomCartPoleVecEnv(RandomEnv):
+    """N domain-randomised cart-poles stepped by hand-written sm_100a kernels."""
+
+    def __init__(self, num_envs, dtype="float32", device=None, seed=0, env_id0=0,
+                 max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, kinematics_integrator="euler",
+                 track_truncated=True, validate_actions=False):
+        RandomEnv.__init__(self)
+        if num_envs <= 0:
+            raise ValueError("num_envs must be positive")
+        self.num_envs = int(num_envs)
+        self._dtype_name = str(dtype).replace("torch.", "")
+        if self._dtype_name not in ("float32", "float64"):
+            raise ValueError("dtype must be float32 or float64")
+        self._device_arg = device
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.env_id0 = int(env_id0)
+        self.max_episode_steps = 0 if max_episode_steps is None else int(max_episode_steps)
+        self.auto_reset = bool(auto_reset)
+        self.kinematics_integrator = kinematics_integrator
+        self.track_truncated = bool(track_truncated)
+        self.validate_actions = bool(validate_actions)
+
+        self.dyn_ind_to_name = dict(enumerate(_TABLE.names))
+        self.original_task = np.array(NOMINAL_TASK)
+        self.task_dim = 4
+        self.min_task = np.zeros(4)
+        self.max_task = np.zeros(4)
+        self.mean_task = np.zeros(4)
+        self.stdev_task = np.zeros(4)
+        self.reward_threshold = _TABLE.reward_threshold
+        self.theta_threshold_radians = THETA_THRESHOLD_RADIANS
+        self.x_threshold = X_THRESHOLD
+        self.force_mag, self.tau = 10.0, 0.02
+        self.polemass_length = 0.05     # frozen, as in the reference (:79 vs :157-166)
+        self._buffers = None
+        self._cfg_cache = None
+        self._step_count = 0
+
+    # ---- xi tables (random_cartpole.py:123-147) ----------------------------------------------------
+    def get_search_bounds_mean(self, index):
+        return _TABLE.search_bounds[index]
+
+    def get_task_lower_bound(self, index):
+        return _TABLE.lower_bounds[index]
+
+    # ---- buffers ----------------------------------------------------------------------------------
+    @property
+    def torch_dtype(self):
+        t = _device.torch()
+        return t.float32 if self._dtype_name == "float32" else t.float64
+
+    @property
+    def device(self):
+        return self._alloc()["device"]
+
+    def _alloc(self):
+        if self._buffers is not None:
+            return self._buffers
+        t = _device.torch()
+        dev = _device.require_cuda(self._device_arg)
+        _lib.load()
+        n, ld = self.num_envs, _round_up(self.num_envs, 32)
+        dt = self.torch_dtype
+        b = dict(device=dev, ld=ld)
+        b["state"] = t.zeros((4, ld), dtype=dt, device=dev)
+        b["xi"] = t.tensor(NOMINAL_TASK, dtype=dt, device=dev).reshape(4, 1).repeat(1, ld).contiguous()
+        b["elapsed"] = t.zeros(ld, dtype=t.int32, device=dev)
+        b["episode"] = t.zeros(ld, dtype=t.int32, device=dev)       # uint32 bit pattern
+        b["beyond"] = t.full((ld,), -1, dtype=t.int32, device=dev)
+        b["reward"] = t.zeros(ld, dtype=dt, device=dev)
+        b["done"] = t.zeros(ld, dtype=t.uint8, device=dev)
+        b["truncated"] = t.zeros(ld, dtype=t.uint8, device=dev)
+        b["action"] = t.zeros(ld, dtype=t.uint8, device=dev)
+        b["stats"] = t.tensor([0.0, 0.0, 0.0, math.inf, -math.inf, 0.0], dtype=t.float64, device=dev)
+        b["env"] = None
+        self._buffers = b
+        self._refresh_env_struct()
+        return b
+
+    def _refresh_env_struct(self):
+        b = self._buffers
+        env = _lib.CartpoleEnv()
+        env.state, env.xi = b["state"].data_ptr(), b["xi"].data_ptr()
+        env.elapsed, env.episode, env.beyond = b["elapsed"].data_ptr(), b["episode"].data_ptr(), b["beyond"].data_ptr()
+        env.n, env.ld = self.num_envs, b["ld"]
+        env.env_id0, env.seed = self.env_id0, self._seed
+        b["env"] = env
+
+    def _suffix(self):
+        return "f32" if self._dtype_name == "float32" else "f64"
+
+    def _integrator(self):
+        return _lib.EULER if self.kinematics_integrator == "euler" else _lib.SEMI_IMPLICIT   # :187-196
+
+    def _on_distribution_change(self):
+        self._cfg_cache = None
+
+    def _active_dr_cfg(self):
+        """DR config used on reset: only when dr_training is on and a distribution is loaded."""
+        if not self.dr_training or self.sampling is None:
+            return None
+        if self._cfg_cache is None:
+            self._cfg_cache = self.dr_config()
+        return ctypes.byref(self._cfg_cache)
+
+    # ---- gym-style API ------------------------------------------------------------------------------
+    def seed(self, seed=None):
+        """Philox key for initial states and DR draws (random_cartpole.py:168-170 returns [seed])."""
+        if seed is None:
+            seed = int(np.random.SeedSequence().entropy % (2 ** 63))
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.seed_dr(self._seed)
+        if self._buffers is not None:
+            self._refresh_env_struct()
+        return [seed]
+
+    def reset(self, mask=None):
+        """Reset every env (or those with mask[i] != 0).  Returns obs (N, 4)."""
+        b = self._alloc()
+        t = _device.torch()
+        mask_ptr = None
+        if mask is not None:
+            mask = t.as_tensor(mask, device=b["device"]).to(t.uint8).contiguous()
+            assert mask.shape == (self.num_envs,)
+            mask_ptr = _device.ptr(mask)
+        viol = self._violation_counter(b["device"])
+        with t.cuda.device(b["device"]):
+            _lib.call("renv_cartpole_reset_" + self._suffix(), ctypes.byref(b["env"]), mask_ptr, self._active_dr_cfg(),
+                      _device.ptr(viol), _device.stream_ptr(b["device"]))
+        return self.obs
+
+    @property
+    def obs(self):
+        b = self._alloc()
+        return b["state"][:, :self.num_envs].t()
+
+    def _stage_actions(self, actions):
+        b = self._buffers
+        t = _device.torch()
+        n = self.num_envs
+        if isinstance(actions, t.Tensor) and actions.is_cuda and actions.dtype == t.uint8 and actions.is_contiguous() \
+                and actions.data_ptr() % 4 == 0 and actions.numel() >= n and actions.dim() == 1:
+            staged = actions
+        else:
+            src = actions if isinstance(actions, t.Tensor) else t.as_tensor(np.asarray(actions))
+            if src.shape != (n,):
+                raise ValueError("actions must have shape (%d,), got %s" % (n, tuple(src.shape)))
+            if src.dtype.is_floating_point:
+                raise AssertionError("%r (%s) invalid" % (actions, type(actions)))   # Discrete(2) rejects floats
+            b["action"][:n].copy_(src, non_blocking=True)
+            staged = b["action"]
+        if self.validate_actions and bool((staged[:n] > 1).any().item()):
+            raise AssertionError("%r (%s) invalid" % (actions, type(actions)))
+        return staged
+
+    def step(self, actions):
+        """One env-step for all N envs.  actions: (N,) integer tensor/array in {0, 1}."""
+        b = self._alloc()
+        t = _device.torch()
+        staged = self._stage_actions(actions)
+        viol = self._violation_counter(b["device"])
+        n = self.num_envs
+        with t.cuda.device(b["device"]):
+            _lib.call("renv_cartpole_step_" + self._suffix(), ctypes.byref(b["env"]), _device.ptr(staged),
+                      _device.ptr(b["reward"]), _device.ptr(b["done"]),
+                      _device.ptr(b["truncated"]) if self.track_truncated else None,
+                      self._integrator(), self.max_episode_steps, int(self.auto_reset), self._active_dr_cfg(),
+                      _device.ptr(viol), _device.stream_ptr(b["device"]))
+        self._step_count += 1
+        info = {}
+        if self.track_truncated:
+            info["TimeLimit.truncated"] = b["truncated"][:n].view(t.bool)
+        return self.obs, b["reward"][:n], b["done"][:n].view(t.bool), info
+
+    def sample_actions(self, out=None):
+        """``action_space.sample()`` for every env: (N,) uint8 Bernoulli(1/2), Philox keyed by step."""
+        b = self._alloc()
+        t = _device.torch()
+        out = b["action"] if out is None else out
+        with t.cuda.device(b["device"]):
+            _lib.call("renv_random_actions_u8", _device.ptr(out), self.num_envs, self.env_id0, self._seed,
+                      self._step_count & 0xFFFFFFFF, _device.stream_ptr(b["device"]))
+        return out[:self.num_envs] if out is b["action"] else out
+
+    def rollout(self, w, b=0.0, num_steps=MAX_EPISODE_STEPS):
+        """K fused env-steps under the in-kernel linear policy a = [w.s + b > 0] (auto-reset always on)."""
+        buf = self._alloc()
+        t = _device.torch()
+        w_arr = (ctypes.c_double * 4)(*[float(v) for v in w])
+        viol = self._violation_counter(buf["device"])
+        with t.cuda.device(buf["device"]):
+            _lib.call("renv_cartpole_rollout_" + self._suffix(), ctypes.byref(buf["env"]), w_arr, float(b),
+                      int(num_steps), self._integrator(), self.max_episode_steps, self._active_dr_cfg(),
+                      _device.ptr(buf["stats"]), _device.ptr(viol), _device.stream_ptr(buf["device"]))
+        self._step_count += int(num_steps)
+
+    @property
+    def stats_tensor(self):
+        """Device tensor [episodes, sum R, sum R^2, min R, max R, sum length] (float64)."""
+        return self._alloc()["stats"]
+
+    def reset_stats(self):
+        t = _device.torch()
+        self._alloc()["stats"].copy_(t.tensor([0.0, 0.0, 0.0, math.inf, -math.inf, 0.0], dtype=t.float64))
+
+    def episode_stats(self):
+        from .distributed import summarize_stats
+        return summarize_stats(self.stats_tensor.cpu().numpy())
+
+    # ---- tasks --------------------------------------------------------------------------------------
+    def get_task(self):
+        return self._alloc()["xi"][:, :self.num_envs].t()
+
+    def set_task(self, *task):
+        """set_task(Tensor(N, 4)) for per-env xi, or set_task(g, m_c, m_p, l) to broadcast one task."""
+        b = self._alloc()
+        t = _device.torch()
+        n = self.num_envs
+        if len(task) == 1:
+            xi = t.as_tensor(task[0], device=b["device"]).to(self.torch_dtype)
+            if xi.shape == (4,):
+                xi = xi.reshape(1, 4).expand(n, 4)
+            if xi.shape != (n, 4):
+                raise ValueError("set_task expects (N, 4) or 4 scalars")
+            b["xi"][:, :n].copy_(xi.t())
+        elif len(task) == 4:
+            b["xi"][:, :n].copy_(t.tensor([float(v) for v in task], dtype=self.torch_dtype,
+                                          device=b["device"]).reshape(4, 1).expand(4, n))
+        else:
+            raise ValueError("set_task expects (N, 4) or 4 scalars")
+
+    def set_random_task(self):
+        """Resample xi of every env now (random_env.py:37-39)."""
+        self.set_task(self.sample_tasks_tensor(self.num_envs, dtype=self.torch_dtype, device=self._alloc()["device"]))
+
+    # ---- host-buffer entry point (end-to-end path: H2D actions, D2H results) -------------------------
+    def step_host(self, actions):
+        """``step`` with HOST buffers: numpy uint8 actions in, numpy (obs, reward, done, truncated) out.
+
+        Copies go through pinned staging buffers on the current stream; one synchronize at the end.
+        """
+        b = self._alloc()
+        t = _device.torch()
+        n = self.num_envs
+        h = b.get("host")
+        if h is None:
+            h = dict(action=t.empty(b["ld"], dtype=t.uint8).pin_memory(),
+                     state=t.empty((4, b["ld"]), dtype=self.torch_dtype).pin_memory(),
+                     reward=t.empty(b["ld"], dtype=self.torch_dtype).pin_memory(),
+                     done=t.empty(b["ld"], dtype=t.uint8).pin_memory(),
+                     truncated=t.empty(b["ld"], dtype=t.uint8).pin_memory())
+            b["host"] = h
+        h["action"][:n].copy_(t.as_tensor(np.asarray(actions, dtype=np.uint8)))
+        b["action"].copy_(h["action"], non_blocking=True)
+        self.step(b["action"])
+        h["state"].copy_(b["state"], non_blocking=True)
+        h["reward"].copy_(b["reward"], non_blocking=True)
+        h["done"].copy_(b["done"], non_blocking=True)
+        if self.track_truncated:
+            h["truncated"].copy_(b["truncated"], non_blocking=True)
+        t.cuda.current_stream(b["device"]).synchronize()
+        return (h["state"].numpy()[:, :n].T, h["reward"].numpy()[:n], h["done"].numpy()[:n].view(np.bool_),
+                h["truncated"].numpy()[:n].view(np.bool_))
+
+    # ---- checkpoint / resume --------------------------------------------------------------------------
+    def state_dict(self):
+        b = self._alloc()
+        keys = ("state", "xi", "elapsed", "episode", "beyond", "stats")
+        out = {k: b[k].clone() for k in keys}
+        out.update(seed=self._seed, env_id0=self.env_id0, step_count=self._step_count, num_envs=self.num_envs,
+                   dtype=self._dtype_name)
+        return out
+
+    def load_state_dict(self, sd):
+        if sd["num_envs"] != self.num_envs or sd["dtype"] != self._dtype_name:
+            raise ValueError("state_dict is for %d %s envs" % (sd["num_envs"], sd["dtype"]))
+        b = self._alloc()
+        for k in ("state", "xi", "elapsed", "episode", "beyond", "stats"):
+            b[k].copy_(sd[k])
+        self._seed, self.env_id0, self._step_count = sd["seed"], sd["env_id0"], sd["step_count"]
+        self._refresh_env_struct()
+
+    # ---- introspection used by tests -------------------------------------------------------------------
+    @property
+    def elapsed(self):
+        return self._alloc()["elapsed"][:self.num_envs]
+
+    @property
+    def episode(self):
+        return self._alloc()["episode"][:self.num_envs]
+
+    @property
+    def steps_beyond_done(self):
+        return self._alloc()["beyond"][:self.num_envs]
+
+    def set_state(self, state, elapsed=None):
+        """Inject per-env states (N, 4) (parity tests: the reference's ``env.state = s0``)."""
+        b = self._alloc()
+        t = _device.torch()
+        st = t.as_tensor(state, device=b["device"]).to(self.torch_dtype)
+        b["state"][:, :self.num_envs].copy_(st.t())
+        b["beyond"].fill_(-1)
+        if elapsed is not None:
+            b["elapsed"][:self.num_envs].copy_(t.as_tensor(elapsed, device=b["device"]).to(t.int32))

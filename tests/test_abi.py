@@ -1,0 +1,75 @@
+"""The C-ABI library loads on a CPU-only machine and exports exactly what include/renv.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from random_envs_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "renv.h")
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(renv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_and_fresh():
+    assert os.path.isfile(build.LIB_PATH), "run python -m random_envs_b200.build"
+    assert not build.is_stale(), "librenv_b200.so is older than its sources"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = _declared()
+    assert len(names) >= 13
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "%s declared in renv.h but not exported" % n
+    assert sorted(_lib.SIGNATURES) == names, "ctypes binding and header disagree"
+    assert _lib.load().renv_abi_version() == _lib.ABI_VERSION == 1
+
+
+def test_header_constants_match_binding():
+    text = open(HEADER).read()
+    assert int(re.search(r"#define RENV_MAX_DIM (\d+)", text).group(1)) == _lib.MAX_DIM
+    assert int(re.search(r"#define RENV_NUM_STATS (\d+)", text).group(1)) == _lib.NUM_STATS
+    assert ctypes.sizeof(_lib.DrCfg) == 8 + 3 * 8 * _lib.MAX_DIM
+    assert ctypes.sizeof(_lib.CartpoleEnv) == 5 * 8 + 4 * 8
+
+
+def test_strerror_and_argument_validation_without_a_gpu():
+    """Negative status codes come from host-side validation, before any CUDA call."""
+    lib = _lib.load()
+    assert _lib.strerror(0) == "ok"
+    assert "NULL" in _lib.strerror(-1) and "Unknown dr_type" in _lib.strerror(-5)
+    cfg = _lib.make_dr_cfg("uniform", [0.0] * 4, [1.0] * 4)
+    assert lib.renv_dr_sample_f32(None, 10, ctypes.byref(cfg), 0, 0, 0, None, None) == -1          # NULL out
+    assert lib.renv_dr_sample_f32(ctypes.c_void_p(256), 0, ctypes.byref(cfg), 0, 0, 0, None, None) == -3   # n <= 0
+    assert lib.renv_dr_sample_f32(ctypes.c_void_p(260), 8, ctypes.byref(cfg), 0, 0, 0, None, None) == -2   # misaligned
+    cfg.dim = 33
+    assert lib.renv_dr_sample_f32(ctypes.c_void_p(256), 8, ctypes.byref(cfg), 0, 0, 0, None, None) == -4
+    cfg.dim, cfg.dr_type = 4, 9
+    assert lib.renv_dr_sample_f32(ctypes.c_void_p(256), 8, ctypes.byref(cfg), 0, 0, 0, None, None) == -5
+    env = _lib.CartpoleEnv()
+    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, None, None, None) == -1
+    env.state = env.xi = env.elapsed = env.episode = 4096
+    env.n, env.ld = 10, 8
+    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, None, None, None) == -3             # ld < n
+    env.ld = 10
+    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, None, None, None) == -2             # ld % 4
+    assert lib.renv_cartpole_reset_f64(ctypes.byref(env), None, None, None, None) != -2             # ld % 2 ok for f64
+    env.ld = 12
+    assert lib.renv_cartpole_step_f32(ctypes.byref(env), 4096, 4096, 4096, None, 7, 500, 1, None, None, None) == -6
+    assert lib.renv_cartpole_step_f32(ctypes.byref(env), 4096, 4096, 4096, None, 0, 500, 0, None, None, None) == -1  # beyond
+    w = (ctypes.c_double * 4)(0, 0, 1, 0)
+    assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 0, 0, 500, None, 4096, None, None) == -3
+    with pytest.raises(_lib.RenvError, match="alignment"):
+        _lib.call("renv_random_actions_u8", ctypes.c_void_p(4100), 16, 0, 0, 0, None)
+
+
+def test_unknown_dr_type_raises_reference_message():
+    with pytest.raises(Exception, match="Unknown dr_type:beta"):
+        _lib.make_dr_cfg("beta", [0.0], [1.0])
