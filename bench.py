@@ -206,7 +206,7 @@ def run_b200(args):
     envs, actions = [], []
     for b in range(R):
         env = renv.RandomCartPoleVecEnv(n, dtype=args.dtype, device=dev, seed=0, env_id0=(rank * R + b) * n,
-                                        track_truncated=False)
+                                        track_truncated=False, track_episodes=False)
         env.set_dr_distribution("uniform", SEARCH)
         env.set_dr_training(True)
         env.reset()
@@ -311,7 +311,7 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
     # single-step kernel at working sets far beyond L2: 2^24 and 2^26 envs, plus fp64 at 2^24
     for label, n, dtype, steps in (("step_f32_16M", 1 << 24, "float32", 40), ("step_f32_64M", 1 << 26, "float32", 12),
                                    ("step_f64_16M", 1 << 24, "float64", 20)):
-        env = renv.RandomCartPoleVecEnv(n, dtype=dtype, device=dev, seed=1, env_id0=rank * n, track_truncated=False)
+        env = renv.RandomCartPoleVecEnv(n, dtype=dtype, device=dev, seed=1, env_id0=rank * n, track_truncated=False, track_episodes=False)
         env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True); env.reset()
         a = env.sample_actions().clone()
         for _ in range(3):

@@ -17,8 +17,11 @@
  *   - Layout: structure-of-arrays.  `state` is (4, ld): rows x, x_dot, theta, theta_dot;
  *     `xi` is (4, ld): rows gravity, cart_mass, pole_mass, pole_length
  *     (order of random_envs/random_cartpole.py:104-107,149-155).
- *   - RNG: counter-based Philox4x32-10, key = seed, counter = (global env id, episode, purpose|slot);
- *     results depend only on (seed, env_id0 + i, episode[i]) -- never on launch geometry or sharding.
+ *   - RNG: counter-based Philox4x32-10, key = seed, counter = (global env id, tick, purpose|slot).  `tick` is
+ *     the caller's step clock (48 bits used): pass a value that grows by 1 per reset/step call and by K per
+ *     K-step rollout (step k of a rollout uses tick + k).  An env starts at most one episode per tick, so
+ *     (seed, env_id0 + i, tick) names the episode; results never depend on launch geometry or sharding,
+ *     and a K-step rollout at tick t equals K single steps at ticks t .. t+K-1 bit for bit.
  */
 #ifndef RENV_B200_H
 #define RENV_B200_H
@@ -72,7 +75,7 @@ typedef struct renv_cartpole_env {
     void *state;                 /* T (4, ld)   RandomCartPoleEnv.state            :176,198 */
     void *xi;                    /* T (4, ld)   gravity, cart_mass, pole_mass, pole_length :157-166 */
     int32_t *elapsed;            /* (n) TimeLimit._elapsed_steps (gym 0.21)                 */
-    uint32_t *episode;           /* (n) Philox episode counter; bumped by every reset       */
+    uint32_t *episode;           /* (n) episodes started per env (statistics only; may be NULL)   */
     int32_t *beyond;             /* (n) steps_beyond_done, -1 == None (:207-222); may be NULL when auto_reset */
     int64_t n;                   /* envs in this shard */
     int64_t ld;                  /* row stride of state/xi in elements, >= n */
@@ -95,10 +98,10 @@ int renv_dr_sample_f64(double *out, int64_t n, const renv_dr_cfg *cfg, uint64_t 
 /* RandomCartPoleEnv.reset (random_cartpole.py:226-229) for every env with mask[i] != 0 (mask NULL = all),
  * preceded by RandomEnv.set_random_task (random_env.py:37-39) when dr != NULL and dr->dr_type != NONE
  * (the README.md:9 / MuJoCo-env behaviour; CartPole's own reset forgets it).  Also zeroes elapsed,
- * sets beyond = -1 and bumps episode. */
-int renv_cartpole_reset_f32(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+ * sets beyond = -1 and counts the new episode. */
+int renv_cartpole_reset_f32(const renv_cartpole_env *env, const uint8_t *mask, uint64_t tick, const renv_dr_cfg *dr,
                             unsigned long long *violations, void *stream);
-int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, uint64_t tick, const renv_dr_cfg *dr,
                             unsigned long long *violations, void *stream);
 
 /* RandomCartPoleEnv.step (random_cartpole.py:172-224) for all n envs, fused with
@@ -107,24 +110,24 @@ int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, c
  * action (n) in {0,1}; reward (n) T; done (n) u8; truncated (n) u8 or NULL.
  * With auto_reset the state written back for a finished env is its reset state (the obs gym returns). */
 int renv_cartpole_step_f32(const renv_cartpole_env *env, const uint8_t *action, float *reward, uint8_t *done,
-                           uint8_t *truncated, int integrator, int max_steps, int auto_reset,
+                           uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
                            const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
 int renv_cartpole_step_f64(const renv_cartpole_env *env, const uint8_t *action, double *reward, uint8_t *done,
-                           uint8_t *truncated, int integrator, int max_steps, int auto_reset,
+                           uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
                            const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
 
 /* K fused steps with the linear policy a = [w.s + b > 0] evaluated in-kernel, auto-reset always on.
  * State, xi and counters stay in registers for the K steps.  stats (device, RENV_NUM_STATS doubles,
  * caller-initialised to {0,0,0,+inf,-inf,0}) is ACCUMULATED with the finished episodes' returns. */
 int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
-                              int max_steps, const renv_dr_cfg *dr, double *stats,
+                              int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,
                               unsigned long long *violations, void *stream);
 int renv_cartpole_rollout_f64(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
-                              int max_steps, const renv_dr_cfg *dr, double *stats,
+                              int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,
                               unsigned long long *violations, void *stream);
 
 /* action_space.sample() for n envs (test_random_policy.py:26): Bernoulli(1/2) bits of Philox block
- * (env_id >> 7, step). */
+ * (env_id >> 7, tick = step). */
 int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step,
                            void *stream);
 

@@ -70,10 +70,10 @@ def philox(ctr, key):
 def init_state(seed, env_id, episode, dtype=np.float64):
     if np.dtype(dtype) == np.float64:
         o = (ctypes.c_double * 4)()
-        lib().oracle_init_state_f64(ctypes.c_uint64(seed), ctypes.c_uint64(env_id), ctypes.c_uint32(episode), o)
+        lib().oracle_init_state_f64(ctypes.c_uint64(seed), ctypes.c_uint64(env_id), ctypes.c_uint64(episode), o)
     else:
         o = (ctypes.c_float * 4)()
-        lib().oracle_init_state_f32(ctypes.c_uint64(seed), ctypes.c_uint64(env_id), ctypes.c_uint32(episode), o)
+        lib().oracle_init_state_f32(ctypes.c_uint64(seed), ctypes.c_uint64(env_id), ctypes.c_uint64(episode), o)
     return np.array(list(o), dtype=dtype)
 
 
@@ -85,7 +85,7 @@ def xi_uniform(seed, sample_id, episode, lo, hi, purpose=PURPOSE_XI, dtype=np.fl
         f, t = lib().oracle_xi_uniform_f64, ctypes.c_double
     else:
         f, t = lib().oracle_xi_uniform_f32, ctypes.c_float
-    f(ctypes.c_uint64(seed), ctypes.c_uint64(sample_id), ctypes.c_uint32(episode), ctypes.c_uint32(purpose),
+    f(ctypes.c_uint64(seed), ctypes.c_uint64(sample_id), ctypes.c_uint64(episode), ctypes.c_uint32(purpose),
       ctypes.c_int(dim), _p(lo, ctypes.c_double), _p(hi, ctypes.c_double), _p(out, t))
     return out
 
@@ -96,7 +96,7 @@ def uniforms(seed, sample_id, episode, purpose, attempt, dim, dtype=np.float64):
         f, t = lib().oracle_uniforms_f64, ctypes.c_double
     else:
         f, t = lib().oracle_uniforms_f32, ctypes.c_float
-    f(ctypes.c_uint64(seed), ctypes.c_uint64(sample_id), ctypes.c_uint32(episode), ctypes.c_uint32(purpose),
+    f(ctypes.c_uint64(seed), ctypes.c_uint64(sample_id), ctypes.c_uint64(episode), ctypes.c_uint32(purpose),
       ctypes.c_int(attempt), ctypes.c_int(dim), _p(out, t))
     return out
 
@@ -104,7 +104,7 @@ def uniforms(seed, sample_id, episode, purpose, attempt, dim, dtype=np.float64):
 def random_actions(n, env_id0, seed, step):
     out = np.zeros(n, dtype=np.uint8)
     lib().oracle_random_actions(ctypes.c_int64(n), ctypes.c_uint64(env_id0), ctypes.c_uint64(seed),
-                                ctypes.c_uint32(step), _p(out, ctypes.c_uint8))
+                                ctypes.c_uint64(step), _p(out, ctypes.c_uint8))
     return out
 
 
@@ -112,9 +112,11 @@ def new_stats():
     return np.array([0.0, 0.0, 0.0, np.inf, -np.inf, 0.0])
 
 
-def closed_loop(state, xi, elapsed, episode, seed, env_id0, K, max_steps=500, euler=True,
+def closed_loop(state, xi, elapsed, episode, seed, env_id0, tick0, K, max_steps=500, euler=True,
                 actions=None, w=None, b=0.0, lo=None, hi=None, stats=None, log=False):
     """Run K steps of step -> TimeLimit -> auto-reset for every env (all arrays updated in place).
+
+    Step k runs at clock ``tick0 + k`` (the framework's RNG contract: a reset is keyed by the tick it happens in).
 
     Returns dict(stats=..., done=(K,n) bool, truncated=(K,n) bool, states=(K,4,n)) (logs only if log=True).
     """
@@ -133,7 +135,7 @@ def closed_loop(state, xi, elapsed, episode, seed, env_id0, K, max_steps=500, eu
     states = np.zeros((K, 4, n), np.float64) if log else None
     lib().oracle_closed_loop_f64(
         ctypes.c_int64(n), _p(state, ctypes.c_double), _p(xi, ctypes.c_double), _p(elapsed, ctypes.c_int32),
-        _p(episode, ctypes.c_uint32), ctypes.c_uint64(seed), ctypes.c_uint64(env_id0), ctypes.c_int(K),
+        _p(episode, ctypes.c_uint32), ctypes.c_uint64(seed), ctypes.c_uint64(env_id0), ctypes.c_uint64(tick0), ctypes.c_int(K),
         ctypes.c_int(max_steps), ctypes.c_int(1 if euler else 0), _p(actions, ctypes.c_uint8),
         _p(w_, ctypes.c_double), ctypes.c_double(b), _p(lo_, ctypes.c_double), _p(hi_, ctypes.c_double),
         _p(stats, ctypes.c_double), _p(done, ctypes.c_uint8), _p(trunc, ctypes.c_uint8), _p(states, ctypes.c_double))

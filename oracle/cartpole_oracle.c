@@ -90,9 +90,12 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 
 enum { PURPOSE_INIT = 0, PURPOSE_XI = 1, PURPOSE_ACTION = 2, PURPOSE_TASKS = 3 };
 
-static void draw(uint64_t seed, uint64_t id, uint32_t episode, uint32_t purpose, uint32_t sub, uint32_t r[4])
+/* counter = (id[31:0], id[47:32] | tick[47:32] << 16, tick[31:0], purpose << 24 | slot); tick = the env's step clock
+ * at the launch that started the episode (DESIGN.md "RNG contract"). */
+static void draw(uint64_t seed, uint64_t id, uint64_t tick, uint32_t purpose, uint32_t sub, uint32_t r[4])
 {
-    uint32_t ctr[4] = { (uint32_t)id, (uint32_t)(id >> 32), episode, (purpose << 24) | sub };
+    uint32_t c1 = ((uint32_t)(id >> 32) & 0xffffu) | (((uint32_t)(tick >> 32) & 0xffffu) << 16);
+    uint32_t ctr[4] = { (uint32_t)id, c1, (uint32_t)tick, (purpose << 24) | sub };
     uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
     oracle_philox4x32_10(ctr, key, r);
 }
@@ -104,13 +107,13 @@ static double u01_f64(uint32_t hi, uint32_t lo)   /* numpy's 53-bit recipe */
 static float u01_f32(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
 
 /* k-th U[0,1) of stream (seed,id,episode,purpose) at attempt t -- fp64 packing: 2 per call */
-static double uniform_f64(uint64_t seed, uint64_t id, uint32_t ep, uint32_t purpose, int t, int k)
+static double uniform_f64(uint64_t seed, uint64_t id, uint64_t ep, uint32_t purpose, int t, int k)
 {
     uint32_t r[4];
     draw(seed, id, ep, purpose, (uint32_t)(t * 16 + k / 2), r);
     return (k & 1) ? u01_f64(r[2], r[3]) : u01_f64(r[0], r[1]);
 }
-static float uniform_f32(uint64_t seed, uint64_t id, uint32_t ep, uint32_t purpose, int t, int k)
+static float uniform_f32(uint64_t seed, uint64_t id, uint64_t ep, uint32_t purpose, int t, int k)
 {
     uint32_t r[4];
     draw(seed, id, ep, purpose, (uint32_t)(t * 16 + k / 4), r);
@@ -118,21 +121,21 @@ static float uniform_f32(uint64_t seed, uint64_t id, uint32_t ep, uint32_t purpo
 }
 
 /* reset draws: s0 ~ U(-0.05, 0.05)^4  (random_cartpole.py:227; numpy: low + (high-low)*u) */
-void oracle_init_state_f64(uint64_t seed, uint64_t id, uint32_t ep, double s[4])
+void oracle_init_state_f64(uint64_t seed, uint64_t id, uint64_t ep, double s[4])
 {
     for (int k = 0; k < 4; ++k) s[k] = -0.05 + 0.1 * uniform_f64(seed, id, ep, PURPOSE_INIT, 0, k);
 }
-void oracle_init_state_f32(uint64_t seed, uint64_t id, uint32_t ep, float s[4])
+void oracle_init_state_f32(uint64_t seed, uint64_t id, uint64_t ep, float s[4])
 {
     for (int k = 0; k < 4; ++k) s[k] = fmaf(0.1f, uniform_f32(seed, id, ep, PURPOSE_INIT, 0, k), -0.05f);
 }
 /* uniform DR draw of one xi vector (random_env.py:151), attempt 0 only */
-void oracle_xi_uniform_f64(uint64_t seed, uint64_t id, uint32_t ep, uint32_t purpose, int dim,
+void oracle_xi_uniform_f64(uint64_t seed, uint64_t id, uint64_t ep, uint32_t purpose, int dim,
                            const double *lo, const double *hi, double *out)
 {
     for (int k = 0; k < dim; ++k) out[k] = lo[k] + (hi[k] - lo[k]) * uniform_f64(seed, id, ep, purpose, 0, k);
 }
-void oracle_xi_uniform_f32(uint64_t seed, uint64_t id, uint32_t ep, uint32_t purpose, int dim,
+void oracle_xi_uniform_f32(uint64_t seed, uint64_t id, uint64_t ep, uint32_t purpose, int dim,
                            const double *lo, const double *hi, float *out)
 {
     for (int k = 0; k < dim; ++k) {
@@ -141,17 +144,17 @@ void oracle_xi_uniform_f32(uint64_t seed, uint64_t id, uint32_t ep, uint32_t pur
     }
 }
 /* raw uniforms, for checking the truncnorm / gaussian transforms against scipy on the host */
-void oracle_uniforms_f64(uint64_t seed, uint64_t id, uint32_t ep, uint32_t purpose, int t, int dim, double *out)
+void oracle_uniforms_f64(uint64_t seed, uint64_t id, uint64_t ep, uint32_t purpose, int t, int dim, double *out)
 {
     for (int k = 0; k < dim; ++k) out[k] = uniform_f64(seed, id, ep, purpose, t, k);
 }
-void oracle_uniforms_f32(uint64_t seed, uint64_t id, uint32_t ep, uint32_t purpose, int t, int dim, float *out)
+void oracle_uniforms_f32(uint64_t seed, uint64_t id, uint64_t ep, uint32_t purpose, int t, int dim, float *out)
 {
     for (int k = 0; k < dim; ++k) out[k] = uniform_f32(seed, id, ep, purpose, t, k);
 }
 
 /* Bernoulli(1/2) actions: env e at step t uses bit (e & 127) of the 128-bit block (e >> 7, t) */
-void oracle_random_actions(int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step, uint8_t *out)
+void oracle_random_actions(int64_t n, uint64_t env_id0, uint64_t seed, uint64_t step, uint8_t *out)
 {
     for (int64_t i = 0; i < n; ++i) {
         uint64_t e = env_id0 + (uint64_t)i;
@@ -163,7 +166,8 @@ void oracle_random_actions(int64_t n, uint64_t env_id0, uint64_t seed, uint32_t 
 
 /* ---- 3. closed loop ------------------------------------------------------------------------ */
 /* One env's worth of: [policy] -> step -> TimeLimit -> auto-reset (+ uniform DR resample).
- * state/xi SoA (4,n); elapsed (n) int32; episode (n) uint32.
+ * state/xi SoA (4,n); elapsed (n) int32; episode (n) uint32 = episodes started (statistics);
+ * step k of the loop runs at clock tick0 + k: that tick keys the Philox draws of a reset happening in it.
  * actions: (K,n) uint8 when w == NULL, else ignored and a = [w.s + b > 0] (left-to-right sum).
  * lo/hi NULL => xi untouched on reset.  max_steps <= 0 => no TimeLimit.
  * stats[6] += {episodes, sum R, sum R^2, min R, max R, sum length}  (min/max start at +/-inf by caller)
@@ -171,7 +175,7 @@ void oracle_random_actions(int64_t n, uint64_t env_id0, uint64_t seed, uint32_t 
  * state returned by step k, i.e. AFTER auto-reset, as the vector env does.
  */
 void oracle_closed_loop_f64(int64_t n, double *state, double *xi, int32_t *elapsed, uint32_t *episode,
-                            uint64_t seed, uint64_t env_id0, int K, int max_steps, int euler,
+                            uint64_t seed, uint64_t env_id0, uint64_t tick0, int K, int max_steps, int euler,
                             const uint8_t *actions, const double *w, double b,
                             const double *lo, const double *hi,
                             double *stats, uint8_t *done_log, uint8_t *trunc_log, double *state_log)
@@ -205,8 +209,8 @@ void oracle_closed_loop_f64(int64_t n, double *state, double *xi, int32_t *elaps
                 if (ret > stats[4]) stats[4] = ret;
                 stats[5] += (double)el;
                 ep += 1; el = 0;
-                if (lo) oracle_xi_uniform_f64(seed, id, ep, PURPOSE_XI, 4, lo, hi, p);
-                oracle_init_state_f64(seed, id, ep, s);
+                if (lo) oracle_xi_uniform_f64(seed, id, tick0 + (uint64_t)k, PURPOSE_XI, 4, lo, hi, p);
+                oracle_init_state_f64(seed, id, tick0 + (uint64_t)k, s);
             }
             if (done_log) done_log[(int64_t)k * n + i] = (uint8_t)done;
             if (trunc_log) trunc_log[(int64_t)k * n + i] = (uint8_t)trunc;

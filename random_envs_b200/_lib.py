@@ -44,12 +44,12 @@ SIGNATURES = {
     "renv_strerror": (ctypes.c_char_p, [_int]),
     "renv_dr_sample_f32": (_int, [_vp, _i64, _cfg_p, _u64, _u64, _u32, _vp, _vp]),
     "renv_dr_sample_f64": (_int, [_vp, _i64, _cfg_p, _u64, _u64, _u32, _vp, _vp]),
-    "renv_cartpole_reset_f32": (_int, [_env_p, _vp, _cfg_p, _vp, _vp]),
-    "renv_cartpole_reset_f64": (_int, [_env_p, _vp, _cfg_p, _vp, _vp]),
-    "renv_cartpole_step_f32": (_int, [_env_p, _vp, _vp, _vp, _vp, _int, _int, _int, _cfg_p, _vp, _vp]),
-    "renv_cartpole_step_f64": (_int, [_env_p, _vp, _vp, _vp, _vp, _int, _int, _int, _cfg_p, _vp, _vp]),
-    "renv_cartpole_rollout_f32": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _cfg_p, _vp, _vp, _vp]),
-    "renv_cartpole_rollout_f64": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _cfg_p, _vp, _vp, _vp]),
+    "renv_cartpole_reset_f32": (_int, [_env_p, _vp, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_reset_f64": (_int, [_env_p, _vp, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_step_f32": (_int, [_env_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_step_f64": (_int, [_env_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_rollout_f32": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
+    "renv_cartpole_rollout_f64": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_random_actions_u8": (_int, [_vp, _i64, _u64, _u64, _u32, _vp]),
     "renv_fma_peak_f32": (_int, [_vp, _int, _int, _int, _vp]),
     "renv_fma_peak_f64": (_int, [_vp, _int, _int, _int, _vp]),

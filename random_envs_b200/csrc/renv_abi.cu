@@ -24,15 +24,13 @@ int to_cfg4(const renv_dr_cfg *dr, DrCfg4 *out)
 
 template <typename T> int check_env(const renv_cartpole_env *env, bool need_beyond, EnvPtrs<T> *out)
 {
-    if (env == nullptr || env->state == nullptr || env->xi == nullptr || env->elapsed == nullptr ||
-        env->episode == nullptr)
-        return RENV_E_NULL;
+    if (env == nullptr || env->state == nullptr || env->xi == nullptr || env->elapsed == nullptr) return RENV_E_NULL;
     if (need_beyond && env->beyond == nullptr) return RENV_E_NULL;
     if (env->n <= 0 || env->ld < env->n) return RENV_E_SIZE;
     constexpr int V = VecTraits<T>::V;
     if (env->ld % V != 0) return RENV_E_ALIGN;
-    if (!aligned(env->state, 16) || !aligned(env->xi, 16) || !aligned(env->elapsed, 16) || !aligned(env->episode, 4) ||
-        (env->beyond && !aligned(env->beyond, 4)))
+    if (!aligned(env->state, 16) || !aligned(env->xi, 16) || !aligned(env->elapsed, 16) ||
+        (env->episode && !aligned(env->episode, 4)) || (env->beyond && !aligned(env->beyond, 4)))
         return RENV_E_ALIGN;
     out->state = static_cast<T *>(env->state);
     out->xi = static_cast<T *>(env->xi);
@@ -70,7 +68,7 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
 }
 
 template <typename T>
-int cartpole_reset(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+int cartpole_reset(const renv_cartpole_env *env, const uint8_t *mask, uint64_t tick, const renv_dr_cfg *dr,
                    unsigned long long *violations, void *stream)
 {
     ResetArgs<T> a;
@@ -79,6 +77,7 @@ int cartpole_reset(const renv_cartpole_env *env, const uint8_t *mask, const renv
     rc = to_cfg4(dr, &a.dr);
     if (rc) return rc;
     a.mask = mask;
+    a.tick = tick;
     a.violations = violations;
     const int64_t blocks = (env->n + 255) / 256;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
@@ -88,7 +87,7 @@ int cartpole_reset(const renv_cartpole_env *env, const uint8_t *mask, const renv
 
 template <typename T>
 int cartpole_step(const renv_cartpole_env *env, const uint8_t *action, T *reward, uint8_t *done, uint8_t *truncated,
-                  int integrator, int max_steps, int auto_reset, const renv_dr_cfg *dr,
+                  int integrator, int max_steps, int auto_reset, uint64_t tick, const renv_dr_cfg *dr,
                   unsigned long long *violations, void *stream)
 {
     StepArgs<T> a;
@@ -103,19 +102,21 @@ int cartpole_step(const renv_cartpole_env *env, const uint8_t *action, T *reward
     a.action = action; a.reward = reward; a.done = done; a.truncated = truncated;
     a.euler = integrator == RENV_EULER;
     a.max_steps = max_steps;
-    a.auto_reset = auto_reset != 0;
+    a.tick = tick;
     a.violations = violations;
-    constexpr int V = VecTraits<T>::V;
-    const int64_t groups = (env->n + V - 1) / V;
-    const int64_t blocks = (groups + 255) / 256;
+    constexpr int64_t per_block = (int64_t)kStepThreads * VecTraits<T>::V;
+    const int64_t blocks = (env->n + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
-    cartpole_step_kernel<T><<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    if (auto_reset)
+        cartpole_step_kernel<T, true><<<(unsigned)blocks, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    else
+        cartpole_step_kernel<T, false><<<(unsigned)blocks, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return launch_status();
 }
 
 template <typename T>
 int cartpole_rollout(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator, int max_steps,
-                     const renv_dr_cfg *dr, double *stats, unsigned long long *violations, void *stream)
+                     uint64_t tick, const renv_dr_cfg *dr, double *stats, unsigned long long *violations, void *stream)
 {
     RolloutArgs<T> a;
     int rc = check_env<T>(env, false, &a.env);
@@ -130,6 +131,7 @@ int cartpole_rollout(const renv_cartpole_env *env, const double w[4], double b, 
     a.K = K;
     a.euler = integrator == RENV_EULER;
     a.max_steps = max_steps;
+    a.tick = tick;
     a.stats = stats;
     a.violations = violations;
     const int64_t blocks = (env->n + kRolloutThreads - 1) / kRolloutThreads;
@@ -178,43 +180,43 @@ int renv_dr_sample_f64(double *out, int64_t n, const renv_dr_cfg *cfg, uint64_t 
     return dr_sample<double>(out, n, cfg, seed, sample_id0, call, violations, stream);
 }
 
-int renv_cartpole_reset_f32(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+int renv_cartpole_reset_f32(const renv_cartpole_env *env, const uint8_t *mask, uint64_t tick, const renv_dr_cfg *dr,
                             unsigned long long *violations, void *stream)
 {
-    return cartpole_reset<float>(env, mask, dr, violations, stream);
+    return cartpole_reset<float>(env, mask, tick, dr, violations, stream);
 }
-int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, const renv_dr_cfg *dr,
+int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, uint64_t tick, const renv_dr_cfg *dr,
                             unsigned long long *violations, void *stream)
 {
-    return cartpole_reset<double>(env, mask, dr, violations, stream);
+    return cartpole_reset<double>(env, mask, tick, dr, violations, stream);
 }
 
 int renv_cartpole_step_f32(const renv_cartpole_env *env, const uint8_t *action, float *reward, uint8_t *done,
-                           uint8_t *truncated, int integrator, int max_steps, int auto_reset, const renv_dr_cfg *dr,
-                           unsigned long long *violations, void *stream)
+                           uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
+                           const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
 {
-    return cartpole_step<float>(env, action, reward, done, truncated, integrator, max_steps, auto_reset, dr,
+    return cartpole_step<float>(env, action, reward, done, truncated, integrator, max_steps, auto_reset, tick, dr,
                                 violations, stream);
 }
 int renv_cartpole_step_f64(const renv_cartpole_env *env, const uint8_t *action, double *reward, uint8_t *done,
-                           uint8_t *truncated, int integrator, int max_steps, int auto_reset, const renv_dr_cfg *dr,
-                           unsigned long long *violations, void *stream)
+                           uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
+                           const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
 {
-    return cartpole_step<double>(env, action, reward, done, truncated, integrator, max_steps, auto_reset, dr,
+    return cartpole_step<double>(env, action, reward, done, truncated, integrator, max_steps, auto_reset, tick, dr,
                                  violations, stream);
 }
 
 int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
-                              int max_steps, const renv_dr_cfg *dr, double *stats, unsigned long long *violations,
-                              void *stream)
+                              int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,
+                              unsigned long long *violations, void *stream)
 {
-    return cartpole_rollout<float>(env, w, b, K, integrator, max_steps, dr, stats, violations, stream);
+    return cartpole_rollout<float>(env, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
 }
 int renv_cartpole_rollout_f64(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
-                              int max_steps, const renv_dr_cfg *dr, double *stats, unsigned long long *violations,
-                              void *stream)
+                              int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,
+                              unsigned long long *violations, void *stream)
 {
-    return cartpole_rollout<double>(env, w, b, K, integrator, max_steps, dr, stats, violations, stream);
+    return cartpole_rollout<double>(env, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
 }
 
 int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step, void *stream)

@@ -9,8 +9,9 @@
 //   double  the PARITY path.  Every operation is an explicitly rounded __d*_rn intrinsic in the
 //           reference's operator order, so nvcc can neither contract to FMA nor reassociate; the only
 //           difference from CPython is sin/cos (CUDA <= 2 ulp vs glibc) and pow(x,2) vs x*x.
-//   float   the THROUGHPUT path.  Same formulae with hand-placed FMAs and 1/total_mass hoisted;
-//           written with intrinsics as well so the result does not depend on which kernel inlines it.
+//   float   the THROUGHPUT path.  Same formulae with hand-placed FMAs, 1/total_mass hoisted, MUFU reciprocals
+//           and a small-angle sin/cos polynomial; written with intrinsics as well so the result does not
+//           depend on which kernel inlines it (fused rollout == repeated single step, bit for bit).
 #pragma once
 #include "renv_dr.cuh"
 
@@ -32,11 +33,39 @@ template <typename T> struct Derived;
 template <> struct Derived<double> { };
 template <> struct Derived<float> { float inv_total_mass, pm_over_total, pml_over_total; };
 
+// MUFU.RCP (<= 1 ulp): the float path trades the last bit of 1/x for one instruction instead of ~8.
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// sin/cos for the float path.  With auto-reset |theta| <= 0.2095 at the start of every step (an env beyond the
+// threshold was reset), so the odd/even Taylor polynomials of degree 7/8 are exact to < 0.2 ulp on |x| <= 0.5
+// (first dropped terms: x^9/9! = 5.4e-9, x^10/10! = 2.7e-10 at 0.5) in ~11 FMA-pipe instructions; anything larger
+// (only reachable when stepping past `done` without auto-reset) takes CUDA's full-range sincosf.
+__device__ __forceinline__ void sincos_small(float x, float *sn, float *cs)
+{
+    if (fabsf(x) <= 0.5f) {
+        const float x2 = __fmul_rn(x, x);
+        float ps = fmaf(x2, -1.0f / 5040.0f, 1.0f / 120.0f);
+        ps = fmaf(x2, ps, -1.0f / 6.0f);
+        *sn = fmaf(__fmul_rn(x, x2), ps, x);
+        float pc = fmaf(x2, 1.0f / 40320.0f, -1.0f / 720.0f);
+        pc = fmaf(x2, pc, 1.0f / 24.0f);
+        pc = fmaf(x2, pc, -0.5f);
+        *cs = fmaf(x2, pc, 1.0f);
+    } else {
+        sincosf(x, sn, cs);
+    }
+}
+
 __device__ __forceinline__ Derived<double> derive(const Xi<double> &) { return {}; }
 __device__ __forceinline__ Derived<float> derive(const Xi<float> &p)
 {
     Derived<float> d;
-    d.inv_total_mass = __frcp_rn(__fadd_rn(p.pole_mass, p.cart_mass));
+    d.inv_total_mass = rcp_approx(__fadd_rn(p.pole_mass, p.cart_mass));
     d.pm_over_total = __fmul_rn(p.pole_mass, d.inv_total_mass);
     d.pml_over_total = __fmul_rn((float)kPolemassLength, d.inv_total_mass);
     return d;
@@ -80,12 +109,12 @@ __device__ __forceinline__ bool dynamics(State<float> &s, const Xi<float> &p, co
 {
     const float force = action == 1 ? (float)kForceMag : -(float)kForceMag;
     float sn, cs;
-    sincosf(s.theta, &sn, &cs);
+    sincos_small(s.theta, &sn, &cs);
     const float temp = __fmul_rn(fmaf(__fmul_rn(s.theta_dot, s.theta_dot), __fmul_rn((float)kPolemassLength, sn), force),
                                  d.inv_total_mass);
     const float num = fmaf(p.gravity, sn, -__fmul_rn(cs, temp));
     const float den = __fmul_rn(p.pole_length, fmaf(-d.pm_over_total, __fmul_rn(cs, cs), (float)kFourThirds));
-    const float theta_acc = __fdiv_rn(num, den);
+    const float theta_acc = __fmul_rn(num, rcp_approx(den));
     const float x_acc = fmaf(-__fmul_rn(d.pml_over_total, cs), theta_acc, temp);
     const float tau = (float)kTau;
     if (euler) {
@@ -125,20 +154,20 @@ __device__ __forceinline__ int policy_action(const Policy<float> &q, const State
 }
 
 // ---- reset: s0 ~ U(-0.05, 0.05)^4 (:227) and, when DR is on, xi ~ sample_task() ---------------------
-__device__ __forceinline__ void init_state(State<float> &s, uint64_t seed, uint64_t id, uint32_t episode)
+__device__ __forceinline__ void init_state(State<float> &s, uint64_t seed, uint64_t id, uint64_t tick)
 {
     float u[4];
-    Pack<float>::uniforms(draw_block(seed, id, episode, kInit, 0), u);
+    Pack<float>::uniforms(draw_block(seed, id, tick, kInit, 0), u);
     s.x = fmaf(0.1f, u[0], -0.05f);
     s.x_dot = fmaf(0.1f, u[1], -0.05f);
     s.theta = fmaf(0.1f, u[2], -0.05f);
     s.theta_dot = fmaf(0.1f, u[3], -0.05f);
 }
-__device__ __forceinline__ void init_state(State<double> &s, uint64_t seed, uint64_t id, uint32_t episode)
+__device__ __forceinline__ void init_state(State<double> &s, uint64_t seed, uint64_t id, uint64_t tick)
 {
     double u[2], v[2];
-    Pack<double>::uniforms(draw_block(seed, id, episode, kInit, 0), u);
-    Pack<double>::uniforms(draw_block(seed, id, episode, kInit, 1), v);
+    Pack<double>::uniforms(draw_block(seed, id, tick, kInit, 0), u);
+    Pack<double>::uniforms(draw_block(seed, id, tick, kInit, 1), v);
     s.x = __dadd_rn(-0.05, __dmul_rn(0.1, u[0]));           // numpy: low + (high - low) * u
     s.x_dot = __dadd_rn(-0.05, __dmul_rn(0.1, u[1]));
     s.theta = __dadd_rn(-0.05, __dmul_rn(0.1, v[0]));
@@ -146,13 +175,13 @@ __device__ __forceinline__ void init_state(State<double> &s, uint64_t seed, uint
 }
 
 template <typename T>
-__device__ __forceinline__ unsigned sample_xi(Xi<T> &p, const DrCfg4 &cfg, uint64_t seed, uint64_t id, uint32_t episode)
+__device__ __forceinline__ unsigned sample_xi(Xi<T> &p, const DrCfg4 &cfg, uint64_t seed, uint64_t id, uint64_t tick)
 {
     constexpr int P = Pack<T>::kPerBlock;
     T v[4] = { p.gravity, p.cart_mass, p.pole_mass, p.pole_length };
     unsigned violations = 0;
 #pragma unroll
-    for (int j = 0; j < 4 / P; ++j) violations += sample_dim_block<T>(cfg, seed, id, episode, kXi, j, v + j * P);
+    for (int j = 0; j < 4 / P; ++j) violations += sample_dim_block<T>(cfg, seed, id, tick, kXi, j, v + j * P);
     p.gravity = v[0]; p.cart_mass = v[1]; p.pole_mass = v[2]; p.pole_length = v[3];
     return violations;
 }

@@ -44,7 +44,7 @@ template <> struct Num<double> {
 
 // Fills out[k] for dims d = j*P + k < dim.  Returns the number of gaussian violations in this block.
 template <typename T, typename Cfg>
-__device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t seed, uint64_t id, uint32_t episode,
+__device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t seed, uint64_t id, uint64_t tick,
                                                      uint32_t purpose, int j, T *out)
 {
     constexpr int P = Pack<T>::kPerBlock;
@@ -52,7 +52,7 @@ __device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t se
     unsigned violations = 0;
     if (cfg.dr_type == kDrUniform) {
         T u[P];
-        Pack<T>::uniforms(draw_block(seed, id, episode, purpose, (uint32_t)j), u);
+        Pack<T>::uniforms(draw_block(seed, id, tick, purpose, (uint32_t)j), u);
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             if (d0 + k < cfg.dim) {
@@ -67,7 +67,7 @@ __device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t se
         for (int k = 0; k < P; ++k)
             if (d0 + k < cfg.dim) pending |= 1u << k;
         for (int t = 0; t < 3 && pending; ++t) {
-            const uint4 r = draw_block(seed, id, episode, purpose, (uint32_t)(t * 16 + j));
+            const uint4 r = draw_block(seed, id, tick, purpose, (uint32_t)(t * 16 + j));
             T z[P];
             if (tn) {
                 Pack<T>::uniforms(r, z);

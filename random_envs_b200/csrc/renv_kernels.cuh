@@ -5,7 +5,8 @@
 // a fully coalesced LDG.E.128 / STG.E.128: per env-step 37 B read + 25 B written in fp32 (62 B),
 // 69 + 45 = 114 B in fp64 (DESIGN.md "algorithmic bytes").  All loads are issued before the first
 // use (10 independent 128-bit requests per thread in flight).  Auto-reset and the DR resample are
-// fused into the same kernel: only envs that finished touch `episode` and rewrite `xi`.
+// fused into the same kernel: only envs that finished rewrite `xi`, and nothing is loaded for a reset
+// (Philox is keyed by the launch's clock tick, not by a per-env counter in HBM).
 #pragma once
 #include <cuda_runtime.h>
 #include "renv_cartpole.cuh"
@@ -44,121 +45,140 @@ template <typename T> struct EnvPtrs {
     int64_t n, ld; uint64_t env_id0, seed;
 };
 
+// RandomCartPoleEnv.reset (+ set_random_task) of env i at clock `tick`; scalar stores.
+template <typename T>
+__device__ __forceinline__ unsigned reset_env(const EnvPtrs<T> &env, const DrCfg4 &dr, int64_t i, uint64_t tick)
+{
+    const int64_t ld = env.ld;
+    const uint64_t id = env.env_id0 + (uint64_t)i;
+    State<T> st;
+    init_state(st, env.seed, id, tick);
+    env.state[0 * ld + i] = st.x; env.state[1 * ld + i] = st.x_dot;
+    env.state[2 * ld + i] = st.theta; env.state[3 * ld + i] = st.theta_dot;
+    unsigned viol = 0;
+    if (dr.dr_type != kDrNone) {
+        Xi<T> xi = { T(0), T(0), T(0), T(0) };
+        viol = sample_xi(xi, dr, env.seed, id, tick);
+        env.xi[0 * ld + i] = xi.gravity; env.xi[1 * ld + i] = xi.cart_mass;
+        env.xi[2 * ld + i] = xi.pole_mass; env.xi[3 * ld + i] = xi.pole_length;
+    }
+    if (env.episode) atomicAdd(env.episode + i, 1u);      // optional episode count: fire-and-forget RED, no load stall
+    return viol;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Single step: RandomCartPoleEnv.step + TimeLimit.step + SyncVectorEnv auto-reset (+ set_random_task)
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct StepArgs {
     EnvPtrs<T> env;
     const uint8_t *action; T *reward; uint8_t *done; uint8_t *truncated;
-    int euler, max_steps, auto_reset;
+    int euler, max_steps;
+    uint64_t tick;
     DrCfg4 dr;
     unsigned long long *violations;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) cartpole_step_kernel(const StepArgs<T> a)
+constexpr int kStepThreads = 256;
+
+// kAutoReset = true is the hot kernel.  Finished envs are NOT reset by the thread that owns them (that would
+// run the ~250-instruction Philox/sampling path once per warp per finished lane with ~1 active lane): their
+// CTA-local indices are appended to a shared-memory list and, after one __syncthreads, the first `count`
+// threads of the CTA each reset one env at full lane utilisation, overwriting the owner's stores.
+template <typename T, bool kAutoReset>
+__global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 2)) cartpole_step_kernel(const StepArgs<T> a)
 {
     using VT = VecTraits<T>;
     constexpr int V = VT::V;
-    const int64_t group = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t i0 = group * V;
+    __shared__ unsigned s_count;
+    __shared__ uint16_t s_list[kAutoReset ? kStepThreads * V : 1];
+    if (kAutoReset) {
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+    }
+    const int64_t block0 = (int64_t)blockIdx.x * (kStepThreads * V);
+    const int64_t i0 = block0 + (int64_t)threadIdx.x * V;
     const int64_t n = a.env.n, ld = a.env.ld;
-    if (i0 >= n) return;
-    const bool full = i0 + V <= n;
 
-    T s[4][V], p[4][V];
-    int32_t el[V];
-    uint8_t act[V];
-    if (full) {
+    if (i0 < n) {
+        const bool full = i0 + V <= n;
+        T s[4][V], p[4][V];
+        int32_t el[V];
+        uint8_t act[V];
+        if (full) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) vload<typename VT::Real>(s[c], a.env.state + c * ld + i0);
+            for (int c = 0; c < 4; ++c) vload<typename VT::Real>(s[c], a.env.state + c * ld + i0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) vload<typename VT::Real>(p[c], a.env.xi + c * ld + i0);
-        vload<typename VT::Int>(el, a.env.elapsed + i0);
-        vload<typename VT::Byte>(act, a.action + i0);
-    } else {
+            for (int c = 0; c < 4; ++c) vload<typename VT::Real>(p[c], a.env.xi + c * ld + i0);
+            vload<typename VT::Int>(el, a.env.elapsed + i0);
+            vload<typename VT::Byte>(act, a.action + i0);
+        } else {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const bool ok = i0 + v < n;
+            for (int v = 0; v < V; ++v) {
+                const bool ok = i0 + v < n;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                s[c][v] = ok ? a.env.state[c * ld + i0 + v] : T(0);
-                p[c][v] = ok ? a.env.xi[c * ld + i0 + v] : T(1);
-            }
-            el[v] = ok ? a.env.elapsed[i0 + v] : 0;
-            act[v] = ok ? a.action[i0 + v] : 0;
-        }
-    }
-
-    T rew[V];
-    uint8_t dn[V], tr[V];
-    unsigned finished = 0;
-    const bool euler = a.euler != 0;
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        State<T> st = { s[0][v], s[1][v], s[2][v], s[3][v] };
-        const Xi<T> xi = { p[0][v], p[1][v], p[2][v], p[3][v] };
-        const bool terminated = dynamics(st, xi, derive(xi), act[v], euler);
-        s[0][v] = st.x; s[1][v] = st.x_dot; s[2][v] = st.theta; s[3][v] = st.theta_dot;
-        el[v] += 1;                                                    // TimeLimit.step
-        bool done = terminated, trunc = false;
-        if (a.max_steps > 0 && el[v] >= a.max_steps) { trunc = !terminated; done = true; }
-        T r = T(1);                                                    // :207-212
-        if (!a.auto_reset && a.env.beyond != nullptr && i0 + v < n && terminated) {
-            const int32_t b = a.env.beyond[i0 + v];                    // :213-222 (only reachable without auto-reset)
-            a.env.beyond[i0 + v] = b < 0 ? 0 : b + 1;
-            r = b < 0 ? T(1) : T(0);
-        }
-        rew[v] = r; dn[v] = done; tr[v] = trunc;
-        if (done && a.auto_reset && i0 + v < n) finished |= 1u << v;
-    }
-
-    // SyncVectorEnv auto-reset (+ set_random_task when DR is on).  Executed max-over-lanes(popc) times per
-    // warp, not V times; no dynamically indexed register arrays (selects only).
-    unsigned viol = 0;
-    while (finished) {
-        const int v = __ffs(finished) - 1;
-        finished &= finished - 1;
-        const int64_t i = i0 + v;
-        const uint64_t id = a.env.env_id0 + (uint64_t)i;
-        const uint32_t ep = a.env.episode[i] + 1u;
-        a.env.episode[i] = ep;
-        State<T> st;
-        init_state(st, a.env.seed, id, ep);
-        Xi<T> xi;
-        const bool resample = a.dr.dr_type != kDrNone;
-        if (resample) {
-            xi = Xi<T>{ T(0), T(0), T(0), T(0) };
-            viol += sample_xi(xi, a.dr, a.env.seed, id, ep);
-            a.env.xi[0 * ld + i] = xi.gravity; a.env.xi[1 * ld + i] = xi.cart_mass;
-            a.env.xi[2 * ld + i] = xi.pole_mass; a.env.xi[3 * ld + i] = xi.pole_length;
-        }
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            if (k == v) { s[0][k] = st.x; s[1][k] = st.x_dot; s[2][k] = st.theta; s[3][k] = st.theta_dot; el[k] = 0; }
-        }
-    }
-    if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
-
-    if (full) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) vstore<typename VT::Real>(a.env.state + c * ld + i0, s[c]);
-        vstore<typename VT::Int>(a.env.elapsed + i0, el);
-        vstore<typename VT::Real>(a.reward + i0, rew);
-        vstore<typename VT::Byte>(a.done + i0, dn);
-        if (a.truncated) vstore<typename VT::Byte>(a.truncated + i0, tr);
-    } else {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            if (i0 + v < n) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) a.env.state[c * ld + i0 + v] = s[c][v];
-                a.env.elapsed[i0 + v] = el[v];
-                a.reward[i0 + v] = rew[v];
-                a.done[i0 + v] = dn[v];
-                if (a.truncated) a.truncated[i0 + v] = tr[v];
+                for (int c = 0; c < 4; ++c) {
+                    s[c][v] = ok ? a.env.state[c * ld + i0 + v] : T(0);
+                    p[c][v] = ok ? a.env.xi[c * ld + i0 + v] : T(1);
+                }
+                el[v] = ok ? a.env.elapsed[i0 + v] : 0;
+                act[v] = ok ? a.action[i0 + v] : 0;
             }
         }
+
+        T rew[V];
+        uint8_t dn[V], tr[V];
+        const bool euler = a.euler != 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            State<T> st = { s[0][v], s[1][v], s[2][v], s[3][v] };
+            const Xi<T> xi = { p[0][v], p[1][v], p[2][v], p[3][v] };
+            const bool terminated = dynamics(st, xi, derive(xi), act[v], euler);
+            s[0][v] = st.x; s[1][v] = st.x_dot; s[2][v] = st.theta; s[3][v] = st.theta_dot;
+            el[v] += 1;                                                    // TimeLimit.step
+            bool done = terminated, trunc = false;
+            if (a.max_steps > 0 && el[v] >= a.max_steps) { trunc = !terminated; done = true; }
+            T r = T(1);                                                    // :207-212
+            if (!kAutoReset && i0 + v < n && terminated) {
+                const int32_t b = a.env.beyond[i0 + v];                    // :213-222 (only reachable without auto-reset)
+                a.env.beyond[i0 + v] = b < 0 ? 0 : b + 1;
+                r = b < 0 ? T(1) : T(0);
+            }
+            rew[v] = r; dn[v] = done; tr[v] = trunc;
+            if (kAutoReset && done && i0 + v < n) {
+                el[v] = 0;
+                s_list[atomicAdd(&s_count, 1u)] = (uint16_t)(threadIdx.x * V + v);
+            }
+        }
+
+        if (full) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) vstore<typename VT::Real>(a.env.state + c * ld + i0, s[c]);
+            vstore<typename VT::Int>(a.env.elapsed + i0, el);
+            vstore<typename VT::Real>(a.reward + i0, rew);
+            vstore<typename VT::Byte>(a.done + i0, dn);
+            if (a.truncated) vstore<typename VT::Byte>(a.truncated + i0, tr);
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                if (i0 + v < n) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) a.env.state[c * ld + i0 + v] = s[c][v];
+                    a.env.elapsed[i0 + v] = el[v];
+                    a.reward[i0 + v] = rew[v];
+                    a.done[i0 + v] = dn[v];
+                    if (a.truncated) a.truncated[i0 + v] = tr[v];
+                }
+            }
+        }
+    }
+
+    if (kAutoReset) {
+        __syncthreads();                    // list complete; the owners' stores above are ordered before ours
+        const unsigned count = s_count;
+        unsigned viol = 0;
+        for (unsigned j = threadIdx.x; j < count; j += kStepThreads)
+            viol += reset_env(a.env, a.dr, block0 + s_list[j], a.tick);
+        if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
     }
 }
 
@@ -168,6 +188,7 @@ __global__ void __launch_bounds__(256) cartpole_step_kernel(const StepArgs<T> a)
 template <typename T> struct ResetArgs {
     EnvPtrs<T> env;
     const uint8_t *mask;
+    uint64_t tick;
     DrCfg4 dr;
     unsigned long long *violations;
 };
@@ -177,23 +198,10 @@ template <typename T> __global__ void __launch_bounds__(256) cartpole_reset_kern
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.env.n) return;
     if (a.mask && !a.mask[i]) return;
-    const int64_t ld = a.env.ld;
-    const uint64_t id = a.env.env_id0 + (uint64_t)i;
-    const uint32_t ep = a.env.episode[i] + 1u;
-    a.env.episode[i] = ep;
     a.env.elapsed[i] = 0;
     if (a.env.beyond) a.env.beyond[i] = -1;
-    State<T> st;
-    init_state(st, a.env.seed, id, ep);
-    a.env.state[0 * ld + i] = st.x; a.env.state[1 * ld + i] = st.x_dot;
-    a.env.state[2 * ld + i] = st.theta; a.env.state[3 * ld + i] = st.theta_dot;
-    if (a.dr.dr_type != kDrNone) {
-        Xi<T> xi = { T(0), T(0), T(0), T(0) };
-        const unsigned viol = sample_xi(xi, a.dr, a.env.seed, id, ep);
-        a.env.xi[0 * ld + i] = xi.gravity; a.env.xi[1 * ld + i] = xi.cart_mass;
-        a.env.xi[2 * ld + i] = xi.pole_mass; a.env.xi[3 * ld + i] = xi.pole_length;
-        if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
-    }
+    const unsigned viol = reset_env(a.env, a.dr, i, a.tick);
+    if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -224,6 +232,7 @@ template <typename T> struct RolloutArgs {
     EnvPtrs<T> env;
     Policy<T> policy;
     int K, euler, max_steps;
+    uint64_t tick;
     DrCfg4 dr;
     double *stats;
     unsigned long long *violations;
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(kRolloutThreads) cartpole_rollout_kernel(const
         Xi<T> p = { a.env.xi[i], a.env.xi[ld + i], a.env.xi[2 * ld + i], a.env.xi[3 * ld + i] };
         Derived<T> d = derive(p);
         int32_t el = a.env.elapsed[i];
-        uint32_t ep = a.env.episode[i];
+        uint32_t new_episodes = 0;
         const uint64_t id = a.env.env_id0 + (uint64_t)i;
         const bool euler = a.euler != 0;
         const bool resample = a.dr.dr_type != kDrNone;
@@ -262,14 +271,15 @@ __global__ void __launch_bounds__(kRolloutThreads) cartpole_rollout_kernel(const
                 episodes += 1; sum_len += (unsigned)el;
                 sum_r += (double)ret; sum_r2 += (double)ret * (double)ret;
                 min_r = fminf(min_r, ret); max_r = fmaxf(max_r, ret);
-                ep += 1; el = 0;
+                new_episodes += 1; el = 0;
+                const uint64_t tick = a.tick + (uint64_t)k;      // the clock value a single step() would use
                 if (resample) {
                     p = Xi<T>{ T(0), T(0), T(0), T(0) };
-                    viol += sample_xi(p, a.dr, a.env.seed, id, ep);
+                    viol += sample_xi(p, a.dr, a.env.seed, id, tick);
                     d = derive(p);
                     xi_dirty = true;
                 }
-                init_state(s, a.env.seed, id, ep);
+                init_state(s, a.env.seed, id, tick);
             }
         }
         a.env.state[i] = s.x; a.env.state[ld + i] = s.x_dot; a.env.state[2 * ld + i] = s.theta;
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(kRolloutThreads) cartpole_rollout_kernel(const
             a.env.xi[3 * ld + i] = p.pole_length;
         }
         a.env.elapsed[i] = el;
-        a.env.episode[i] = ep;
+        if (a.env.episode && new_episodes) a.env.episode[i] += new_episodes;
     }
 
     // warp shuffle -> shared -> one set of atomics per CTA

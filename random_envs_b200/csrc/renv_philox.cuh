@@ -5,9 +5,13 @@
 // and s0 from a per-env RandomState (random_cartpole.py:227) -- a serial, stateful design.  Here
 // every random number is a pure function of
 //     key     = (seed lo, seed hi)
-//     counter = (id lo, id hi, episode, purpose << 24 | slot)
-// so any thread can produce any env's draws with no state in HBM beyond the 4-byte episode counter,
-// and results are independent of launch geometry and of how envs are sharded across GPUs.
+//     counter = (id[31:0], id[47:32] | tick[47:32] << 16, tick[31:0], purpose << 24 | slot)
+// where `id` is the GLOBAL env (or sample) index and `tick` identifies the episode: it is the value of
+// the env's step clock at the launch that (re)started the episode -- a host-side counter that advances
+// by one per step / reset call and by K per K-step rollout.  An env starts at most one episode per tick,
+// so (seed, id, tick) is unique per episode, needs NO per-env RNG state in HBM (a per-env episode
+// counter would have to be loaded before the first Philox round: a dependent DRAM round trip inside the
+// reset path), and is independent of launch geometry and of how envs are sharded across GPUs.
 #pragma once
 #include <stdint.h>
 
@@ -29,11 +33,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
     return c;
 }
 
-// One 128-bit block of the stream (seed, id, episode, purpose); slot = attempt * 16 + dim_block.
-__device__ __forceinline__ uint4 draw_block(uint64_t seed, uint64_t id, uint32_t episode, uint32_t purpose,
-                                            uint32_t slot)
+// One 128-bit block of the stream (seed, id, tick, purpose); slot = attempt * 16 + dim_block.
+__device__ __forceinline__ uint4 draw_block(uint64_t seed, uint64_t id, uint64_t tick, uint32_t purpose, uint32_t slot)
 {
-    return philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), episode, (purpose << 24) | slot),
+    const uint32_t c1 = ((uint32_t)(id >> 32) & 0xffffu) | (((uint32_t)(tick >> 32) & 0xffffu) << 16);
+    return philox4x32_10(make_uint4((uint32_t)id, c1, (uint32_t)tick, (purpose << 24) | slot),
                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 

@@ -44,7 +44,7 @@ class RandomCartPoleVecEnv(RandomEnv):
 
     def __init__(self, num_envs, dtype="float32", device=None, seed=0, env_id0=0,
                  max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, kinematics_integrator="euler",
-                 track_truncated=True, validate_actions=False):
+                 track_truncated=True, validate_actions=False, track_episodes=True):
         RandomEnv.__init__(self)
         if num_envs <= 0:
             raise ValueError("num_envs must be positive")
@@ -60,6 +60,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         self.kinematics_integrator = kinematics_integrator
         self.track_truncated = bool(track_truncated)
         self.validate_actions = bool(validate_actions)
+        self.track_episodes = bool(track_episodes)
 
         self.dyn_ind_to_name = dict(enumerate(_TABLE.names))
         self.original_task = np.array(NOMINAL_TASK)
@@ -75,7 +76,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         self.polemass_length = 0.05     # frozen, as in the reference (:79 vs :157-166)
         self._buffers = None
         self._cfg_cache = None
-        self._step_count = 0
+        self._tick = 0                  # step clock: Philox episode key; +1 per reset/step, +K per rollout
 
     # ---- xi tables (random_cartpole.py:123-147) ----------------------------------------------------
     def get_search_bounds_mean(self, index):
@@ -122,7 +123,8 @@ class RandomCartPoleVecEnv(RandomEnv):
         b = self._buffers
         env = _lib.CartpoleEnv()
         env.state, env.xi = b["state"].data_ptr(), b["xi"].data_ptr()
-        env.elapsed, env.episode, env.beyond = b["elapsed"].data_ptr(), b["episode"].data_ptr(), b["beyond"].data_ptr()
+        env.elapsed, env.beyond = b["elapsed"].data_ptr(), b["beyond"].data_ptr()
+        env.episode = b["episode"].data_ptr() if self.track_episodes else None
         env.n, env.ld = self.num_envs, b["ld"]
         env.env_id0, env.seed = self.env_id0, self._seed
         b["env"] = env
@@ -166,8 +168,9 @@ class RandomCartPoleVecEnv(RandomEnv):
             mask_ptr = _device.ptr(mask)
         viol = self._violation_counter(b["device"])
         with t.cuda.device(b["device"]):
-            _lib.call("renv_cartpole_reset_" + self._suffix(), ctypes.byref(b["env"]), mask_ptr, self._active_dr_cfg(),
-                      _device.ptr(viol), _device.stream_ptr(b["device"]))
+            _lib.call("renv_cartpole_reset_" + self._suffix(), ctypes.byref(b["env"]), mask_ptr, self._tick,
+                      self._active_dr_cfg(), _device.ptr(viol), _device.stream_ptr(b["device"]))
+        self._tick += 1
         return self.obs
 
     @property
@@ -205,22 +208,22 @@ class RandomCartPoleVecEnv(RandomEnv):
             _lib.call("renv_cartpole_step_" + self._suffix(), ctypes.byref(b["env"]), _device.ptr(staged),
                       _device.ptr(b["reward"]), _device.ptr(b["done"]),
                       _device.ptr(b["truncated"]) if self.track_truncated else None,
-                      self._integrator(), self.max_episode_steps, int(self.auto_reset), self._active_dr_cfg(),
-                      _device.ptr(viol), _device.stream_ptr(b["device"]))
-        self._step_count += 1
+                      self._integrator(), self.max_episode_steps, int(self.auto_reset), self._tick,
+                      self._active_dr_cfg(), _device.ptr(viol), _device.stream_ptr(b["device"]))
+        self._tick += 1
         info = {}
         if self.track_truncated:
             info["TimeLimit.truncated"] = b["truncated"][:n].view(t.bool)
         return self.obs, b["reward"][:n], b["done"][:n].view(t.bool), info
 
     def sample_actions(self, out=None):
-        """``action_space.sample()`` for every env: (N,) uint8 Bernoulli(1/2), Philox keyed by step."""
+        """``action_space.sample()`` for every env: (N,) uint8 Bernoulli(1/2), Philox keyed by the step clock."""
         b = self._alloc()
         t = _device.torch()
         out = b["action"] if out is None else out
         with t.cuda.device(b["device"]):
             _lib.call("renv_random_actions_u8", _device.ptr(out), self.num_envs, self.env_id0, self._seed,
-                      self._step_count & 0xFFFFFFFF, _device.stream_ptr(b["device"]))
+                      self._tick & 0xFFFFFFFF, _device.stream_ptr(b["device"]))
         return out[:self.num_envs] if out is b["action"] else out
 
     def rollout(self, w, b=0.0, num_steps=MAX_EPISODE_STEPS):
@@ -231,9 +234,9 @@ class RandomCartPoleVecEnv(RandomEnv):
         viol = self._violation_counter(buf["device"])
         with t.cuda.device(buf["device"]):
             _lib.call("renv_cartpole_rollout_" + self._suffix(), ctypes.byref(buf["env"]), w_arr, float(b),
-                      int(num_steps), self._integrator(), self.max_episode_steps, self._active_dr_cfg(),
+                      int(num_steps), self._integrator(), self.max_episode_steps, self._tick, self._active_dr_cfg(),
                       _device.ptr(buf["stats"]), _device.ptr(viol), _device.stream_ptr(buf["device"]))
-        self._step_count += int(num_steps)
+        self._tick += int(num_steps)
 
     @property
     def stats_tensor(self):
@@ -308,7 +311,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         b = self._alloc()
         keys = ("state", "xi", "elapsed", "episode", "beyond", "stats")
         out = {k: b[k].clone() for k in keys}
-        out.update(seed=self._seed, env_id0=self.env_id0, step_count=self._step_count, num_envs=self.num_envs,
+        out.update(seed=self._seed, env_id0=self.env_id0, tick=self._tick, num_envs=self.num_envs,
                    dtype=self._dtype_name)
         return out
 
@@ -318,7 +321,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         b = self._alloc()
         for k in ("state", "xi", "elapsed", "episode", "beyond", "stats"):
             b[k].copy_(sd[k])
-        self._seed, self.env_id0, self._step_count = sd["seed"], sd["env_id0"], sd["step_count"]
+        self._seed, self.env_id0, self._tick = sd["seed"], sd["env_id0"], sd["tick"]
         self._refresh_env_struct()
 
     # ---- introspection used by tests -------------------------------------------------------------------

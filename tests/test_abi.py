@@ -54,18 +54,19 @@ def test_strerror_and_argument_validation_without_a_gpu():
     cfg.dim, cfg.dr_type = 4, 9
     assert lib.renv_dr_sample_f32(ctypes.c_void_p(256), 8, ctypes.byref(cfg), 0, 0, 0, None, None) == -5
     env = _lib.CartpoleEnv()
-    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, None, None, None) == -1
+    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, 0, None, None, None) == -1
     env.state = env.xi = env.elapsed = env.episode = 4096
     env.n, env.ld = 10, 8
-    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, None, None, None) == -3             # ld < n
+    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, 0, None, None, None) == -3             # ld < n
     env.ld = 10
-    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, None, None, None) == -2             # ld % 4
-    assert lib.renv_cartpole_reset_f64(ctypes.byref(env), None, None, None, None) != -2             # ld % 2 ok for f64
+    assert lib.renv_cartpole_reset_f32(ctypes.byref(env), None, 0, None, None, None) == -2             # ld % 4
+    env.ld = 11
+    assert lib.renv_cartpole_reset_f64(ctypes.byref(env), None, 0, None, None, None) == -2             # ld % 2 for f64
     env.ld = 12
-    assert lib.renv_cartpole_step_f32(ctypes.byref(env), 4096, 4096, 4096, None, 7, 500, 1, None, None, None) == -6
-    assert lib.renv_cartpole_step_f32(ctypes.byref(env), 4096, 4096, 4096, None, 0, 500, 0, None, None, None) == -1  # beyond
+    assert lib.renv_cartpole_step_f32(ctypes.byref(env), 4096, 4096, 4096, None, 7, 500, 1, 0, None, None, None) == -6
+    assert lib.renv_cartpole_step_f32(ctypes.byref(env), 4096, 4096, 4096, None, 0, 500, 0, 0, None, None, None) == -1  # beyond
     w = (ctypes.c_double * 4)(0, 0, 1, 0)
-    assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 0, 0, 500, None, 4096, None, None) == -3
+    assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 0, 0, 500, 0, None, 4096, None, None) == -3
     with pytest.raises(_lib.RenvError, match="alignment"):
         _lib.call("renv_random_actions_u8", ctypes.c_void_p(4100), 16, 0, 0, 0, None)
 

@@ -117,7 +117,7 @@ def test_timelimit_truncation_and_auto_reset(golden_dir):
             assert int(env.elapsed[0]) == k + 1
     assert bool(done[0]) and bool(info["TimeLimit.truncated"][0]) and float(rew[0]) == 1.0
     assert int(env.elapsed[0]) == 0 and int(env.episode[0]) == 2
-    want = c_oracle.init_state(11, 0, 2)                                     # the obs returned is the RESET obs
+    want = c_oracle.init_state(11, 0, 500)           # the obs returned is the RESET obs, keyed by the tick of step 500
     assert np.array_equal(_np(obs)[0], want)
 
 
@@ -161,14 +161,14 @@ def test_fp64_closed_loop_with_auto_reset_and_uniform_dr_vs_c_oracle():
     env.set_dr_training(True)
     obs0 = _np(env.reset()).copy()
     xi0 = _np(env.get_task()).copy()
-    # the oracle starts from the same reset (episode 1 of the same Philox streams)
+    # the oracle starts from the same reset: reset() ran at clock tick 0, the K steps run at ticks 1 .. K
     for i in (0, 1, n - 1):
-        assert np.array_equal(obs0[i], c_oracle.init_state(seed, i, 1))
-        assert np.array_equal(xi0[i], c_oracle.xi_uniform(seed, i, 1, lo, hi))
+        assert np.array_equal(obs0[i], c_oracle.init_state(seed, i, 0))
+        assert np.array_equal(xi0[i], c_oracle.xi_uniform(seed, i, 0, lo, hi))
     st = np.ascontiguousarray(obs0.T); xi = np.ascontiguousarray(xi0.T)
     el = np.zeros(n, np.int32); ep = np.ones(n, np.uint32)
-    actions = np.stack([c_oracle.random_actions(n, 0, seed, k) for k in range(K)])
-    out = c_oracle.closed_loop(st, xi, el, ep, seed, 0, K, max_steps=60, actions=actions, lo=lo, hi=hi, log=True)
+    actions = np.stack([c_oracle.random_actions(n, 0, seed, 1 + k) for k in range(K)])
+    out = c_oracle.closed_loop(st, xi, el, ep, seed, 0, 1, K, max_steps=60, actions=actions, lo=lo, hi=hi, log=True)
     worst = 0.0
     for k in range(K):
         a = env.sample_actions()

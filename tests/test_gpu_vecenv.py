@@ -151,7 +151,7 @@ def test_fp64_rollout_vs_c_oracle_closed_loop():
     obs0 = _np(env.reset()).copy(); xi0 = _np(env.get_task()).copy()
     st = np.ascontiguousarray(obs0.T); xi = np.ascontiguousarray(xi0.T)
     el = np.zeros(n, np.int32); ep = np.ones(n, np.uint32)
-    out = c_oracle.closed_loop(st, xi, el, ep, seed, 0, 30, max_steps=500, w=np.array(w), b=b, lo=LO, hi=HI)
+    out = c_oracle.closed_loop(st, xi, el, ep, seed, 0, 1, 30, max_steps=500, w=np.array(w), b=b, lo=LO, hi=HI)
     env.rollout(w, b, 30)
     same = (_np(env.episode).astype(np.uint32) == ep) & (_np(env.elapsed) == el)
     assert same.mean() >= 0.9999, same.mean()      # a near-tie |w.s| ~ 1e-16 may flip one action in ~1e5 envs
@@ -159,7 +159,7 @@ def test_fp64_rollout_vs_c_oracle_closed_loop():
     assert np.array_equal(_np(env.get_task())[same], xi.T[same])
     got = _np(env.stats_tensor).copy()
     assert abs(got[0] - out["stats"][0]) <= 3 and abs(got[1] - out["stats"][1]) <= 300
-    out = c_oracle.closed_loop(st, xi, el, ep, seed, 0, 470, max_steps=500, w=np.array(w), b=b, lo=LO, hi=HI,
+    out = c_oracle.closed_loop(st, xi, el, ep, seed, 0, 31, 470, max_steps=500, w=np.array(w), b=b, lo=LO, hi=HI,
                                stats=out["stats"])
     env.rollout(w, b, 470)
     got = _np(env.stats_tensor); want = out["stats"]
@@ -223,6 +223,20 @@ def test_masked_reset_set_task_and_checkpoint_roundtrip():
         a = env.sample_actions().clone()
         o1, _, d1, _ = env.step(a); o2, _, d2, _ = twin.step(a)
         assert torch.equal(o1, o2) and torch.equal(d1, d2)
+
+
+def test_large_env_ids_and_ticks_follow_the_oracle_contract():
+    """Global env ids beyond 2^32 (shards of a huge job) and clocks beyond 2^32 steps key distinct streams."""
+    base = (1 << 33) + 12345
+    for dtype, npdt in (("float64", np.float64), ("float32", np.float32)):
+        env = _dr_env(64, dtype, seed=17, env_id0=base)
+        env._tick = (1 << 40) + 7
+        obs = _np(env.reset()); xi = _np(env.get_task())
+        for i in (0, 63):
+            assert np.array_equal(obs[i], c_oracle.init_state(17, base + i, (1 << 40) + 7, npdt))
+            assert np.array_equal(xi[i], c_oracle.xi_uniform(17, base + i, (1 << 40) + 7, LO, HI, dtype=npdt))
+        a = env.sample_actions()
+        assert np.array_equal(_np(a), c_oracle.random_actions(64, base, 17, ((1 << 40) + 8) & 0xFFFFFFFF))
 
 
 def test_step_host_matches_step():

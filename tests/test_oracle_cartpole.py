@@ -94,7 +94,7 @@ def test_timelimit_survivor(golden_dir):
     # C closed loop reproduces it with its own in-loop policy (left-to-right dot product)
     st = g["s0"].reshape(4, 1).copy(); xi = g["xi"].reshape(4, 1).copy()
     el = np.zeros(1, np.int32); ep = np.ones(1, np.uint32)
-    out = c_oracle.closed_loop(st, xi, el, ep, seed=7, env_id0=0, K=500, w=g["w"], b=0.0, log=True)
+    out = c_oracle.closed_loop(st, xi, el, ep, seed=7, env_id0=0, tick0=1, K=500, w=g["w"], b=0.0, log=True)
     assert np.array_equal(out["states"][:499, :, 0], g["states"][:499])
     assert out["done"][:499].sum() == 0 and out["done"][499, 0] and out["truncated"][499, 0]
     assert list(out["stats"]) == [1.0, 500.0, 250000.0, 500.0, 500.0, 500.0]
@@ -128,6 +128,10 @@ def test_c_draw_spec():
     assert s.shape == (4,) and np.all(s >= -0.05) and np.all(s < 0.05)
     assert not np.array_equal(s, c_oracle.init_state(3, 11, 2))
     assert not np.array_equal(s, c_oracle.init_state(3, 12, 1))
+    # 48-bit env ids and 48-bit ticks both reach the Philox counter
+    assert not np.array_equal(c_oracle.init_state(3, 11, 5), c_oracle.init_state(3, 11, (1 << 32) + 5))
+    assert not np.array_equal(c_oracle.init_state(3, 11, 5), c_oracle.init_state(3, (1 << 32) + 11, 5))
+    assert not np.array_equal(c_oracle.init_state(3, (1 << 32) + 11, 5), c_oracle.init_state(3, 11, (1 << 32) + 5))
     s32 = c_oracle.init_state(3, 11, 1, np.float32)
     assert s32.dtype == np.float32 and np.all(np.abs(s32) <= 0.05)
     a = c_oracle.random_actions(4096, 0, 0, 0)
