@@ -230,20 +230,38 @@ def run_b200(args):
     K = args.steps
     ms_eager = timed(lambda: [step_i(i) for i in range(K)])
 
-    # the same K steps as one CUDA graph
-    graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(K):
-                step_i(i)
-    torch.cuda.current_stream().wait_stream(side)
-    graph.replay()                                  # untimed: first launch uploads the graph
-    torch.cuda.synchronize()
+    # the same K steps as one CUDA graph.  `chain`: one stream, launches strictly serialised.  `branches`: the R
+    # independent env batches on R parallel graph branches, so one batch's tail wave overlaps another's head
+    # (a 2^20-env launch is only 1.7 waves of CTAs).
+    def capture(parallel):
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                if not parallel:
+                    for i in range(K):
+                        step_i(i)
+                else:
+                    lanes = [torch.cuda.Stream(device=dev) for _ in range(R)]
+                    for b, lane in enumerate(lanes):
+                        lane.wait_stream(side)
+                        with torch.cuda.stream(lane):
+                            for i in range(b, K, R):
+                                step_i(i)
+                    for lane in lanes:
+                        side.wait_stream(lane)
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()                                  # untimed: first launch uploads the graph
+        torch.cuda.synchronize()
+        return g
+
+    reps = 3
+    chain = capture(False)
+    ms_chain = sorted(timed(chain.replay) for _ in range(reps))[reps // 2]
+    graph = capture(True)
 
     clocks = ClockSampler(local_rank).start() if rank == 0 else None
-    reps = 3
     t_wall0 = time.time()
     ms_runs = [timed(graph.replay) for _ in range(reps)]
     # keep the GPU under the same load for >= 0.5 s so that nvidia-smi gets samples of the timed workload
@@ -294,8 +312,13 @@ def run_b200(args):
             "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e, "gpu_launches": K,
-            "launch_mode": "one CUDA graph of K cartpole_step_kernel launches, median of %d replays" % reps,
-            "value_eager": value_eager, "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras}
+            "launch_mode": "one CUDA graph of K cartpole_step_kernel launches, the %d independent env batches on %d "
+                           "parallel graph branches; launch_us = timed region / K; median of %d replays" % (R, R, reps),
+            "value_eager": value_eager, "value_graph_single_chain": world * n * K / (ms_chain * 1e-3),
+            "roofline_single_chain": {"launch_us": 1e3 * ms_chain / K,
+                                      "achieved": BYTES_PER_STEP[args.dtype] * n / (ms_chain / K * 1e-3) / 1e9,
+                                      "frac": BYTES_PER_STEP[args.dtype] * n / (ms_chain / K * 1e-3) / 1e9 / peak},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras}
     print(json.dumps(line), flush=True)
     return 0
 

@@ -91,27 +91,30 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 2)) cartpo
     constexpr int V = VT::V;
     __shared__ unsigned s_count;
     __shared__ uint16_t s_list[kAutoReset ? kStepThreads * V : 1];
-    if (kAutoReset) {
-        if (threadIdx.x == 0) s_count = 0;
-        __syncthreads();
-    }
     const int64_t block0 = (int64_t)blockIdx.x * (kStepThreads * V);
     const int64_t i0 = block0 + (int64_t)threadIdx.x * V;
     const int64_t n = a.env.n, ld = a.env.ld;
+    const bool live = i0 < n;
+    const bool full = i0 + V <= n;
 
-    if (i0 < n) {
-        const bool full = i0 + V <= n;
-        T s[4][V], p[4][V];
-        int32_t el[V];
-        uint8_t act[V];
-        if (full) {
+    T s[4][V], p[4][V];
+    int32_t el[V];
+    uint8_t act[V];
+    if (full) {     // all ten 128-bit requests go out before anything waits (incl. the barrier below)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) vload<typename VT::Real>(s[c], a.env.state + c * ld + i0);
+        for (int c = 0; c < 4; ++c) vload<typename VT::Real>(s[c], a.env.state + c * ld + i0);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) vload<typename VT::Real>(p[c], a.env.xi + c * ld + i0);
-            vload<typename VT::Int>(el, a.env.elapsed + i0);
-            vload<typename VT::Byte>(act, a.action + i0);
-        } else {
+        for (int c = 0; c < 4; ++c) vload<typename VT::Real>(p[c], a.env.xi + c * ld + i0);
+        vload<typename VT::Int>(el, a.env.elapsed + i0);
+        vload<typename VT::Byte>(act, a.action + i0);
+    }
+    if (kAutoReset) {
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();            // overlaps the loads' latency
+    }
+
+    if (live) {
+        if (!full) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const bool ok = i0 + v < n;
