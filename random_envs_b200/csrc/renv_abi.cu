@@ -59,9 +59,10 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
     c.dr_type = cfg->dr_type;
     c.dim = cfg->dim;
     for (int k = 0; k < 32; ++k) { c.a[k] = cfg->a[k]; c.b[k] = cfg->b[k]; c.lb[k] = cfg->lb[k]; }
-    const int64_t blocks = (n + kTileSamples - 1) / kTileSamples;
+    constexpr int kTile = tile_samples<T>();
+    const int64_t blocks = (n + kTile - 1) / kTile;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
-    const size_t smem = (size_t)kTileSamples * cfg->dim * sizeof(T);
+    const size_t smem = (size_t)kTile * cfg->dim * sizeof(T);     // <= 32 KB
     dr_sample_kernel<T><<<(unsigned)blocks, kSampleThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         out, n, c, seed, sample_id0, call, violations);
     return launch_status();

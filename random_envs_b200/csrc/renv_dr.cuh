@@ -8,6 +8,11 @@
 //                        counter-based generator an unused draw has no effect, so attempts 0..2 suffice.)
 //   gaussian   :173-190  X = randn*std + mean; while X < 0.1 redraw; three failures -> the reference raises;
 //                        here the dim is counted in `violations` and set to the floor, the host raises.
+//
+// double: library normcdfinv / log / sincospi with explicitly rounded affine maps (parity path).
+// float:  the truncation to [-2, 2] keeps the inverse CDF in its central region, so Phi^-1 is one MUFU.LG2 and a
+//         degree-6 polynomial (no tail branches, max abs error 2.9e-7 = 1.2 ulp at |z| = 2); Box-Muller uses the
+//         MUFU log / sin / cos / rsqrt approximations (abs error ~2^-21, far below anything a DR law can resolve).
 #pragma once
 #include "renv_philox.cuh"
 
@@ -30,7 +35,37 @@ template <typename T> struct Num;
 template <> struct Num<float> {
     __device__ static __forceinline__ float affine(float scale, float u, float off) { return fmaf(scale, u, off); }
     __device__ static __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    __device__ static __forceinline__ float ndtri(float p) { return normcdfinvf(p); }
+    // z = Phi^-1(Phi(-2) + u * (Phi(2) - Phi(-2))), u in [0, 1).  With x = 2p - 1 in [-X, X], X = Phi(2) - Phi(-2),
+    // z = sqrt(2) erfinv(x) = x * g(w), w = -ln(1 - x^2) in [0, 2.42]; g is fitted (Chebyshev nodes, degree 6 in
+    // t = w - 1.25).  1 - |x| is formed from s = min(u, 1-u) (exact in fp32) to avoid cancellation near |z| = 2.
+    __device__ static __forceinline__ float tn_z(float u)
+    {
+        const float X = (float)kPhiSpan;
+        const float s = fminf(u, __fsub_rn(1.0f, u));
+        const float a = fmaf(2.0f * X, s, 1.0f - X);              // 1 - |x|
+        const float b = __fsub_rn(2.0f, a);                        // 1 + |x|
+        const float t = fmaf(__log2f(__fmul_rn(a, b)), -0.69314718056f, -1.25f);
+        float g = -6.496782899e-06f;
+        g = fmaf(g, t, 4.291892561e-05f);
+        g = fmaf(g, t, 2.023686373e-04f);
+        g = fmaf(g, t, -3.186480695e-03f);
+        g = fmaf(g, t, 3.552299202e-03f);
+        g = fmaf(g, t, 3.528738932e-01f);
+        g = fmaf(g, t, 1.682294103e+00f);
+        const float z = __fmul_rn(g, __fsub_rn(1.0f, a));
+        return u >= 0.5f ? z : -z;
+    }
+    // 4 standard normals from one Philox block: Box-Muller on the pairs (x,y) and (z,w), both branches used
+    __device__ static __forceinline__ void normals(uint4 r, float z[4])
+    {
+        const float two_pi = 6.283185307179586f;
+        float rad = __fsqrt_rn(-2.0f * __logf(u01_open0(r.x)));
+        float ang = two_pi * (u01(r.y) - 0.5f);
+        z[0] = rad * __cosf(ang); z[1] = rad * __sinf(ang);
+        rad = __fsqrt_rn(-2.0f * __logf(u01_open0(r.z)));
+        ang = two_pi * (u01(r.w) - 0.5f);
+        z[2] = rad * __cosf(ang); z[3] = rad * __sinf(ang);
+    }
 };
 template <> struct Num<double> {
     // separately rounded multiply and add: the numpy expression lo + (hi-lo)*u, bit for bit
@@ -39,50 +74,65 @@ template <> struct Num<double> {
         return __dadd_rn(off, __dmul_rn(scale, u));
     }
     __device__ static __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    __device__ static __forceinline__ double ndtri(double p) { return normcdfinv(p); }
+    __device__ static __forceinline__ double tn_z(double u) { return normcdfinv(affine(kPhiSpan, u, kPhiMinus2)); }
+    __device__ static __forceinline__ void normals(uint4 r, double z[2]) { Pack<double>::normals(r, z); }
 };
 
-// Fills out[k] for dims d = j*P + k < dim.  Returns the number of gaussian violations in this block.
-template <typename T, typename Cfg>
-__device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t seed, uint64_t id, uint64_t tick,
-                                                     uint32_t purpose, int j, T *out)
+// Parameters of one dim block (dims j*P .. j*P+P-1) held in registers, already converted to T.
+template <typename T> struct DimBlock {
+    static constexpr int P = Pack<T>::kPerBlock;
+    T a[P], b[P], floor[P];      // floor: lower bound (truncnorm) / 0.1 (gaussian) / unused (uniform)
+    unsigned valid;              // bit k set <=> dim j*P + k exists
+};
+
+template <typename T, typename Cfg> __device__ __forceinline__ DimBlock<T> load_dim_block(const Cfg &cfg, int j)
 {
     constexpr int P = Pack<T>::kPerBlock;
-    const int d0 = j * P;
+    DimBlock<T> blk;
+    blk.valid = 0;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        const int d = j * P + k;
+        const bool ok = d < cfg.dim;
+        blk.a[k] = ok ? (T)cfg.a[d] : T(0);
+        blk.b[k] = ok ? (T)cfg.b[d] : T(0);
+        blk.floor[k] = ok ? (cfg.dr_type == kDrTruncnorm ? (T)cfg.lb[d] : (T)kGaussianFloor) : T(0);
+        if (ok) blk.valid |= 1u << k;
+    }
+    return blk;
+}
+
+// Fills out[k] for the valid dims of the block.  Returns the number of gaussian violations.
+template <typename T>
+__device__ __forceinline__ unsigned sample_dim_block(int dr_type, const DimBlock<T> &blk, uint64_t seed, uint64_t id,
+                                                     uint64_t tick, uint32_t purpose, int j, T *out)
+{
+    constexpr int P = Pack<T>::kPerBlock;
     unsigned violations = 0;
-    if (cfg.dr_type == kDrUniform) {
+    if (dr_type == kDrUniform) {
         T u[P];
         Pack<T>::uniforms(draw_block(seed, id, tick, purpose, (uint32_t)j), u);
 #pragma unroll
-        for (int k = 0; k < P; ++k) {
-            if (d0 + k < cfg.dim) {
-                const T lo = (T)cfg.a[d0 + k], hi = (T)cfg.b[d0 + k];
-                out[k] = Num<T>::affine(Num<T>::sub(hi, lo), u[k], lo);
-            }
-        }
-    } else if (cfg.dr_type == kDrTruncnorm || cfg.dr_type == kDrGaussian) {
-        const bool tn = cfg.dr_type == kDrTruncnorm;
-        unsigned pending = 0;
-#pragma unroll
         for (int k = 0; k < P; ++k)
-            if (d0 + k < cfg.dim) pending |= 1u << k;
+            if (blk.valid & (1u << k)) out[k] = Num<T>::affine(Num<T>::sub(blk.b[k], blk.a[k]), u[k], blk.a[k]);
+    } else if (dr_type == kDrTruncnorm || dr_type == kDrGaussian) {
+        const bool tn = dr_type == kDrTruncnorm;
+        unsigned pending = blk.valid;
         for (int t = 0; t < 3 && pending; ++t) {
             const uint4 r = draw_block(seed, id, tick, purpose, (uint32_t)(t * 16 + j));
             T z[P];
             if (tn) {
                 Pack<T>::uniforms(r, z);
 #pragma unroll
-                for (int k = 0; k < P; ++k)
-                    z[k] = Num<T>::ndtri(Num<T>::affine((T)kPhiSpan, z[k], (T)kPhiMinus2));
+                for (int k = 0; k < P; ++k) z[k] = Num<T>::tn_z(z[k]);
             } else {
-                Pack<T>::normals(r, z);
+                Num<T>::normals(r, z);
             }
 #pragma unroll
             for (int k = 0; k < P; ++k) {
                 if (pending & (1u << k)) {
-                    const T x = Num<T>::affine((T)cfg.b[d0 + k], z[k], (T)cfg.a[d0 + k]);
-                    const T floor_k = tn ? (T)cfg.lb[d0 + k] : (T)kGaussianFloor;
-                    if (!(x < floor_k)) {        // the reference's loop condition is `obs < bound`
+                    const T x = Num<T>::affine(blk.b[k], z[k], blk.a[k]);
+                    if (!(x < blk.floor[k])) {        // the reference's loop condition is `obs < bound`
                         out[k] = x;
                         pending &= ~(1u << k);
                     }
@@ -92,12 +142,19 @@ __device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t se
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             if (pending & (1u << k)) {
-                out[k] = tn ? (T)cfg.lb[d0 + k] : (T)kGaussianFloor;
+                out[k] = blk.floor[k];
                 if (!tn) ++violations;
             }
         }
     }
     return violations;
+}
+
+template <typename T, typename Cfg>
+__device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t seed, uint64_t id, uint64_t tick,
+                                                     uint32_t purpose, int j, T *out)
+{
+    return sample_dim_block<T>(cfg.dr_type, load_dim_block<T>(cfg, j), seed, id, tick, purpose, j, out);
 }
 
 }  // namespace renv

@@ -341,11 +341,14 @@ __global__ void __launch_bounds__(kRolloutThreads) cartpole_rollout_kernel(const
 // doubles = one Philox call); values go to a shared-memory tile that is contiguous in the output, so
 // the tile is written back with fully coalesced 128-bit stores whatever `dim` is (30 is not a
 // multiple of 4: a thread-per-sample store would touch 32 sectors per instruction).
-constexpr int kTileSamples = 128;
 constexpr int kSampleThreads = 256;
+template <typename T> __host__ __device__ constexpr int tile_samples() { return 1024 / (int)sizeof(T); }   // 256 float / 128 double rows
 
 struct DrCfgFull { int dr_type; int dim; double a[32]; double b[32]; double lb[32]; };
 
+// Thread t owns dim block j = t % jpad (jpad = blocks per sample rounded up to a power of two) for the whole
+// kernel, so its distribution parameters are read and converted ONCE into registers and the sample loop is
+// Philox + transform + 4 shared-memory stores, with shifts instead of divisions.
 template <typename T>
 __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict__ out, int64_t n, const DrCfgFull cfg,
                                                                    uint64_t seed, uint64_t sample_id0, uint32_t call,
@@ -354,19 +357,27 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *tile = reinterpret_cast<T *>(smem_raw);
     constexpr int P = Pack<T>::kPerBlock;
+    constexpr int kTile = tile_samples<T>();
     const int dim = cfg.dim;
     const int blocks_per_sample = (dim + P - 1) / P;
-    const int64_t first = (int64_t)blockIdx.x * kTileSamples;
-    const int samples = (int)min((int64_t)kTileSamples, n - first);
-    const int items = samples * blocks_per_sample;
+    int log2pad = 0;
+    while ((1 << log2pad) < blocks_per_sample) ++log2pad;
+    const int j = threadIdx.x & ((1 << log2pad) - 1);
+    const int lane_sample = threadIdx.x >> log2pad, samples_per_pass = kSampleThreads >> log2pad;
+    const int64_t first = (int64_t)blockIdx.x * kTile;
+    const int samples = (int)min((int64_t)kTile, n - first);
     unsigned viol = 0;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int sidx = it / blocks_per_sample, j = it - sidx * blocks_per_sample;
-        T v[P];
-        viol += sample_dim_block<T>(cfg, seed, sample_id0 + (uint64_t)(first + sidx), call, kTasks, j, v);
+    if (j < blocks_per_sample) {
+        const DimBlock<T> blk = load_dim_block<T>(cfg, j);
+        const int dr_type = cfg.dr_type;
+        for (int sidx = lane_sample; sidx < samples; sidx += samples_per_pass) {
+            T v[P];
+            viol += sample_dim_block<T>(dr_type, blk, seed, sample_id0 + (uint64_t)(first + sidx), call, kTasks, j, v);
+            T *row = tile + sidx * dim + j * P;
 #pragma unroll
-        for (int k = 0; k < P; ++k)
-            if (j * P + k < dim) tile[sidx * dim + j * P + k] = v[k];
+            for (int k = 0; k < P; ++k)
+                if (blk.valid & (1u << k)) row[k] = v[k];
+        }
     }
     if (viol && violations) atomicAdd(violations, (unsigned long long)viol);
     __syncthreads();
