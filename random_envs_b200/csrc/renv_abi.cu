@@ -137,7 +137,10 @@ int cartpole_rollout(const renv_cartpole_env *env, const double w[4], double b, 
     a.violations = violations;
     const int64_t blocks = (env->n + kRolloutThreads - 1) / kRolloutThreads;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
-    cartpole_rollout_kernel<T><<<(unsigned)blocks, kRolloutThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    if (a.euler)
+        cartpole_rollout_kernel<T, true><<<(unsigned)blocks, kRolloutThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    else
+        cartpole_rollout_kernel<T, false><<<(unsigned)blocks, kRolloutThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return launch_status();
 }
 

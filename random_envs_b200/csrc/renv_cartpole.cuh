@@ -31,7 +31,12 @@ template <typename T> struct State { T x, x_dot, theta, theta_dot; };
 // Loop-invariant (per episode) quantities of the float path.
 template <typename T> struct Derived;
 template <> struct Derived<double> { };
-template <> struct Derived<float> { float inv_total_mass, pm_over_total, pml_over_total; };
+template <> struct Derived<float> {
+    float force_over_total;     // force_mag / M
+    float pml_over_total;       // polemass_length / M
+    float len_four_thirds;      // l * 4/3
+    float len_pm_over_total;    // l * m_p / M
+};
 
 // MUFU.RCP (<= 1 ulp): the float path trades the last bit of 1/x for one instruction instead of ~8.
 __device__ __forceinline__ float rcp_approx(float x)
@@ -42,18 +47,19 @@ __device__ __forceinline__ float rcp_approx(float x)
 }
 
 // sin/cos for the float path.  With auto-reset |theta| <= 0.2095 at the start of every step (an env beyond the
-// threshold was reset), so the odd/even Taylor polynomials of degree 7/8 are exact to < 0.2 ulp on |x| <= 0.5
-// (first dropped terms: x^9/9! = 5.4e-9, x^10/10! = 2.7e-10 at 0.5) in ~11 FMA-pipe instructions; anything larger
-// (only reachable when stepping past `done` without auto-reset) takes CUDA's full-range sincosf.
+// threshold was reset), so the odd/even Taylor polynomials of degree 5/6 are exact to < 0.5 ulp on |x| <= 0.25
+// (first dropped terms: x^7/7! = 1.2e-8 vs sin(0.25) = 0.247, x^8/8! = 3.8e-10 vs cos ~ 0.97) in 8 FMA-pipe
+// instructions; anything larger (only reachable from an injected state or when stepping past `done` without
+// auto-reset) takes CUDA's full-range sincosf.
+constexpr float kSmallAngle = 0.25f;
+template <bool kKnownSmall = false>
 __device__ __forceinline__ void sincos_small(float x, float *sn, float *cs)
 {
-    if (fabsf(x) <= 0.5f) {
+    if (kKnownSmall || fabsf(x) <= kSmallAngle) {   // kKnownSmall: the caller guarantees it (no branch at all)
         const float x2 = __fmul_rn(x, x);
-        float ps = fmaf(x2, -1.0f / 5040.0f, 1.0f / 120.0f);
-        ps = fmaf(x2, ps, -1.0f / 6.0f);
+        const float ps = fmaf(x2, 1.0f / 120.0f, -1.0f / 6.0f);
         *sn = fmaf(__fmul_rn(x, x2), ps, x);
-        float pc = fmaf(x2, 1.0f / 40320.0f, -1.0f / 720.0f);
-        pc = fmaf(x2, pc, 1.0f / 24.0f);
+        float pc = fmaf(x2, -1.0f / 720.0f, 1.0f / 24.0f);
         pc = fmaf(x2, pc, -0.5f);
         *cs = fmaf(x2, pc, 1.0f);
     } else {
@@ -65,13 +71,16 @@ __device__ __forceinline__ Derived<double> derive(const Xi<double> &) { return {
 __device__ __forceinline__ Derived<float> derive(const Xi<float> &p)
 {
     Derived<float> d;
-    d.inv_total_mass = rcp_approx(__fadd_rn(p.pole_mass, p.cart_mass));
-    d.pm_over_total = __fmul_rn(p.pole_mass, d.inv_total_mass);
-    d.pml_over_total = __fmul_rn((float)kPolemassLength, d.inv_total_mass);
+    const float inv_total_mass = rcp_approx(__fadd_rn(p.pole_mass, p.cart_mass));
+    d.force_over_total = __fmul_rn((float)kForceMag, inv_total_mass);
+    d.pml_over_total = __fmul_rn((float)kPolemassLength, inv_total_mass);
+    d.len_four_thirds = __fmul_rn(p.pole_length, (float)kFourThirds);
+    d.len_pm_over_total = __fmul_rn(p.pole_length, __fmul_rn(p.pole_mass, inv_total_mass));
     return d;
 }
 
 // ---- dynamics: returns terminated -----------------------------------------------------------------
+template <bool kKnownSmall = false>
 __device__ __forceinline__ bool dynamics(State<double> &s, const Xi<double> &p, const Derived<double> &, int action,
                                          bool euler)
 {
@@ -104,16 +113,17 @@ __device__ __forceinline__ bool dynamics(State<double> &s, const Xi<double> &p, 
     return s.x < -kXThreshold || s.x > kXThreshold || s.theta < -kThetaThreshold || s.theta > kThetaThreshold;  // :200-205
 }
 
+template <bool kKnownSmall = false>
 __device__ __forceinline__ bool dynamics(State<float> &s, const Xi<float> &p, const Derived<float> &d, int action,
                                          bool euler)
 {
-    const float force = action == 1 ? (float)kForceMag : -(float)kForceMag;
     float sn, cs;
-    sincos_small(s.theta, &sn, &cs);
-    const float temp = __fmul_rn(fmaf(__fmul_rn(s.theta_dot, s.theta_dot), __fmul_rn((float)kPolemassLength, sn), force),
-                                 d.inv_total_mass);
+    sincos_small<kKnownSmall>(s.theta, &sn, &cs);
+    // temp = (F + pml thd^2 sin) / M ; thetaacc = (g sin - cos temp) / (l (4/3 - m_p cos^2 / M)) ; xacc = temp - pml thetaacc cos / M
+    const float push = action == 1 ? d.force_over_total : -d.force_over_total;
+    const float temp = fmaf(__fmul_rn(__fmul_rn(s.theta_dot, s.theta_dot), sn), d.pml_over_total, push);
     const float num = fmaf(p.gravity, sn, -__fmul_rn(cs, temp));
-    const float den = __fmul_rn(p.pole_length, fmaf(-d.pm_over_total, __fmul_rn(cs, cs), (float)kFourThirds));
+    const float den = fmaf(-d.len_pm_over_total, __fmul_rn(cs, cs), d.len_four_thirds);
     const float theta_acc = __fmul_rn(num, rcp_approx(den));
     const float x_acc = fmaf(-__fmul_rn(d.pml_over_total, cs), theta_acc, temp);
     const float tau = (float)kTau;
@@ -146,11 +156,11 @@ __device__ __forceinline__ int policy_action(const Policy<double> &q, const Stat
 }
 __device__ __forceinline__ int policy_action(const Policy<float> &q, const State<float> &s)
 {
-    float acc = __fmul_rn(q.w0, s.x);
+    float acc = fmaf(q.w0, s.x, q.b);
     acc = fmaf(q.w1, s.x_dot, acc);
     acc = fmaf(q.w2, s.theta, acc);
     acc = fmaf(q.w3, s.theta_dot, acc);
-    return __fadd_rn(acc, q.b) > 0.0f;
+    return acc > 0.0f;
 }
 
 // ---- reset: s0 ~ U(-0.05, 0.05)^4 (:227) and, when DR is on, xi ~ sample_task() ---------------------
