@@ -278,11 +278,8 @@ class RandomCartPoleVecEnv(RandomEnv):
         self.set_task(self.sample_tasks_tensor(self.num_envs, dtype=self.torch_dtype, device=self._alloc()["device"]))
 
     # ---- host-buffer entry point (end-to-end path: H2D actions, D2H results) -------------------------
-    def step_host(self, actions):
-        """``step`` with HOST buffers: numpy uint8 actions in, numpy (obs, reward, done, truncated) out.
-
-        Copies go through pinned staging buffers on the current stream; one synchronize at the end.
-        """
+    def host_buffers(self):
+        """Pinned host staging buffers (numpy views): write ``action`` in place to skip one host memcpy."""
         b = self._alloc()
         t = _device.torch()
         n = self.num_envs
@@ -293,18 +290,51 @@ class RandomCartPoleVecEnv(RandomEnv):
                      reward=t.empty(b["ld"], dtype=self.torch_dtype).pin_memory(),
                      done=t.empty(b["ld"], dtype=t.uint8).pin_memory(),
                      truncated=t.empty(b["ld"], dtype=t.uint8).pin_memory())
+            h["np"] = dict(action=h["action"].numpy()[:n], obs=h["state"].numpy()[:, :n].T,
+                           reward=h["reward"].numpy()[:n], done=h["done"].numpy()[:n].view(np.bool_),
+                           truncated=h["truncated"].numpy()[:n].view(np.bool_))
+            h["stream"] = t.cuda.Stream(device=b["device"])
+            h["event"] = t.cuda.Event()
             b["host"] = h
-        h["action"][:n].copy_(t.as_tensor(np.asarray(actions, dtype=np.uint8)))
-        b["action"].copy_(h["action"], non_blocking=True)
-        self.step(b["action"])
-        h["state"].copy_(b["state"], non_blocking=True)
-        h["reward"].copy_(b["reward"], non_blocking=True)
-        h["done"].copy_(b["done"], non_blocking=True)
-        if self.track_truncated:
-            h["truncated"].copy_(b["truncated"], non_blocking=True)
-        t.cuda.current_stream(b["device"]).synchronize()
-        return (h["state"].numpy()[:, :n].T, h["reward"].numpy()[:n], h["done"].numpy()[:n].view(np.bool_),
-                h["truncated"].numpy()[:n].view(np.bool_))
+        return h["np"]
+
+    def step_host_async(self, actions=None):
+        """Enqueue one host-buffer step (H2D actions -> step kernel -> D2H obs/reward/done[/truncated]) on this
+        env's private stream and return immediately; ``step_host_wait`` returns the numpy results.
+
+        ``actions``: numpy/sequence of {0,1} copied into the pinned staging buffer, or None when the caller has
+        already written ``host_buffers()['action']``.  Several envs can have steps in flight at once, which
+        overlaps one env's device->host transfer with another's host->device transfer and kernel.
+        """
+        views = self.host_buffers()
+        b = self._buffers
+        h = b["host"]
+        t = _device.torch()
+        if actions is not None:
+            np.copyto(views["action"], np.asarray(actions), casting="unsafe")
+        stream = h["stream"]
+        stream.wait_stream(t.cuda.current_stream(b["device"]))
+        with t.cuda.stream(stream):
+            b["action"].copy_(h["action"], non_blocking=True)
+            self.step(b["action"])
+            h["state"].copy_(b["state"], non_blocking=True)
+            h["reward"].copy_(b["reward"], non_blocking=True)
+            h["done"].copy_(b["done"], non_blocking=True)
+            if self.track_truncated:
+                h["truncated"].copy_(b["truncated"], non_blocking=True)
+            h["event"].record(stream)
+
+    def step_host_wait(self):
+        """Block until the last ``step_host_async`` finished -> (obs (N,4), reward, done, truncated) numpy views."""
+        h = self._buffers["host"]
+        h["event"].synchronize()
+        v = h["np"]
+        return v["obs"], v["reward"], v["done"], v["truncated"]
+
+    def step_host(self, actions):
+        """``step`` with HOST buffers: numpy uint8 actions in, numpy (obs, reward, done, truncated) out."""
+        self.step_host_async(actions)
+        return self.step_host_wait()
 
     # ---- checkpoint / resume --------------------------------------------------------------------------
     def state_dict(self):
