@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RENV_ABI_VERSION 1
+#define RENV_ABI_VERSION 2
 #define RENV_MAX_DIM 32          /* largest task_dim in the suite is 30 (jinja/random_humanoid.py) */
 #define RENV_NUM_STATS 6         /* episodes, sum R, sum R^2, min R, max R, sum length */
 
@@ -52,7 +52,8 @@ enum renv_dr_type {
     RENV_DR_NONE = 0,            /* sampling is None / dr_training False: xi is left alone on reset */
     RENV_DR_UNIFORM = 1,         /* random_env.py:150-151 */
     RENV_DR_TRUNCNORM = 2,       /* random_env.py:153-171 */
-    RENV_DR_GAUSSIAN = 3         /* random_env.py:173-190 */
+    RENV_DR_GAUSSIAN = 3,        /* random_env.py:173-190 */
+    RENV_DR_FULLGAUSSIAN = 4     /* random_env.py:192-198 + denormalize_parameters :205-220 */
 };
 
 /* random_envs/random_cartpole.py:187-196: 'euler' vs anything else. */
@@ -61,13 +62,17 @@ enum renv_integrator { RENV_EULER = 0, RENV_SEMI_IMPLICIT = 1 };
 /* Host-side image of RandomEnv's distribution state (random_env.py:102-121 de-interleaved):
  *   uniform:            a = min_task,  b = max_task
  *   truncnorm/gaussian: a = mean_task, b = stdev_task
- *   lb[i] = get_task_lower_bound(i) (used by truncnorm only; gaussian's floor is the literal 0.1). */
+ *   lb[i] = get_task_lower_bound(i) (used by truncnorm only; gaussian's floor is the literal 0.1).
+ *   fullgaussian:       a = mean_task in the normalised [0, 4] space, b / lb = get_task_search_bounds() lo / hi,
+ *                       factor = row-major dim x dim matrix F with F F^T = cov_task (e.g. its Cholesky factor):
+ *                       xi = denormalize(clip(a + F z, 0, 4)), z ~ N(0, I). */
 typedef struct renv_dr_cfg {
     int32_t dr_type;
     int32_t dim;
     double a[RENV_MAX_DIM];
     double b[RENV_MAX_DIM];
     double lb[RENV_MAX_DIM];
+    double factor[RENV_MAX_DIM * RENV_MAX_DIM];
 } renv_dr_cfg;
 
 /* One shard of cart-pole envs resident in HBM (device pointers, element type T = float | double). */

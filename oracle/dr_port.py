@@ -143,3 +143,23 @@ def ks_distance(samples, cdf):
     f_right = cdf(v)
     f_left = cdf(np.nextafter(v, -np.inf))
     return float(max(np.max(np.abs(right - f_right)), np.max(np.abs(left - f_left))))
+
+
+# ----------------------------------------------------------------------------- fullgaussian (random_env.py:192-220)
+def denormalize(p, lo, hi):
+    """``denormalize_parameters`` (:205-220): (p * (hi - lo)) / 4 + lo, p in the normalised [0, 4] space."""
+    p, lo, hi = np.asarray(p, float), np.asarray(lo, float), np.asarray(hi, float)
+    return (p * (hi - lo)) / 4 + lo
+
+
+def sample_fullgaussian_from_z(mean, factor, lo, hi, z):
+    """The law of ``sample_task`` for 'fullgaussian' on explicit standard normals z (..., dim):
+    multivariate normal in the normalised space (:194), clip to [0, 4] (:195), denormalise (:197)."""
+    x = np.asarray(mean, float) + np.asarray(z, float) @ np.asarray(factor, float).T
+    return denormalize(np.clip(x, 0, 4), lo, hi)
+
+
+def box_muller_f64(u_radius_open0, u_angle):
+    """The framework's fp64 normal pair: sqrt(-2 ln u1) * (cos, sin)(2 pi u2), u1 in (0,1], u2 in [0,1)."""
+    rad = np.sqrt(-2.0 * np.log(u_radius_open0))
+    return rad * np.cos(2.0 * np.pi * u_angle), rad * np.sin(2.0 * np.pi * u_angle)

@@ -16,7 +16,8 @@ Files written
   cartpole_timelimit.npz       a 500-step survivor (bang-bang on theta) for the TimeLimit edge
   sampler_control_flow.json    scripted-draw known answers for the truncnorm / gaussian retry loops
   sampler_reference_draws.npz  iid draws of the reference's own sample_task (uniform, gaussian,
-                               truncnorm incl. a lower-bound point-mass case) for two-sample KS
+                               truncnorm incl. a lower-bound point-mass case, fullgaussian with clipping)
+                               for two-sample KS
 """
 import json
 import os
@@ -184,6 +185,14 @@ def sampler_reference_draws(n=4000):
     out["truncnorm_params"] = np.array(t)
     out["truncnorm_lb"] = np.array([env.get_task_lower_bound(i) for i in range(4)])
     out["truncnorm"] = env.sample_tasks(n)
+    # fullgaussian: normalised-space mean/cov (random_env.py:123-127,192-198); dim 3 has a wide variance so that
+    # the clip to [0, 4] is exercised on both sides
+    mean = np.array([2.0, 1.0, 3.0, 2.0])
+    a = np.array([[0.30, 0.00, 0.00, 0.00], [0.10, 0.25, 0.00, 0.00], [-0.05, 0.08, 0.20, 0.00], [0.40, -0.30, 0.20, 1.50]])
+    cov = a @ a.T
+    env.set_dr_distribution("fullgaussian", {"mean": mean, "cov": cov})
+    out["fullgaussian_mean"], out["fullgaussian_cov"] = mean, cov
+    out["fullgaussian"] = env.sample_tasks(n)
     return out
 
 

@@ -7,15 +7,16 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librenv_b200.so")
+LIB_PATH = os.environ.get("RENV_B200_LIB", os.path.join(_HERE, "librenv_b200.so"))   # override: kernel experiments
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_DIM = 32
 NUM_STATS = 6
 
 OK = 0
-DR_NONE, DR_UNIFORM, DR_TRUNCNORM, DR_GAUSSIAN = 0, 1, 2, 3
-DR_TYPE_IDS = {"uniform": DR_UNIFORM, "truncnorm": DR_TRUNCNORM, "gaussian": DR_GAUSSIAN}
+DR_NONE, DR_UNIFORM, DR_TRUNCNORM, DR_GAUSSIAN, DR_FULLGAUSSIAN = 0, 1, 2, 3, 4
+DR_TYPE_IDS = {"uniform": DR_UNIFORM, "truncnorm": DR_TRUNCNORM, "gaussian": DR_GAUSSIAN,
+               "fullgaussian": DR_FULLGAUSSIAN}
 EULER, SEMI_IMPLICIT = 0, 1
 
 
@@ -23,7 +24,7 @@ class DrCfg(ctypes.Structure):
     """struct renv_dr_cfg (include/renv.h)."""
     _fields_ = [("dr_type", ctypes.c_int32), ("dim", ctypes.c_int32),
                 ("a", ctypes.c_double * MAX_DIM), ("b", ctypes.c_double * MAX_DIM),
-                ("lb", ctypes.c_double * MAX_DIM)]
+                ("lb", ctypes.c_double * MAX_DIM), ("factor", ctypes.c_double * (MAX_DIM * MAX_DIM))]
 
 
 class CartpoleEnv(ctypes.Structure):
@@ -101,8 +102,11 @@ def call(name, *args):
         raise RenvError(name, rc, strerror(rc))
 
 
-def make_dr_cfg(dr_type, a, b, lb=None):
-    """Host image of a DR distribution.  dr_type: str key of set_dr_distribution or None."""
+def make_dr_cfg(dr_type, a, b, lb=None, factor=None):
+    """Host image of a DR distribution.  dr_type: str key of set_dr_distribution or None.
+
+    fullgaussian: a = mean (normalised space), b / lb = search-bound lo / hi, factor = (dim, dim) F with F F^T = cov.
+    """
     cfg = DrCfg()
     if dr_type is None:
         cfg.dr_type, cfg.dim = DR_NONE, 0
@@ -117,4 +121,8 @@ def make_dr_cfg(dr_type, a, b, lb=None):
         cfg.a[i] = float(a[i])
         cfg.b[i] = float(b[i])
         cfg.lb[i] = float(lb[i]) if lb is not None else 0.0
+    if factor is not None:
+        for i in range(dim):
+            for k in range(dim):
+                cfg.factor[i * dim + k] = float(factor[i][k])
     return cfg

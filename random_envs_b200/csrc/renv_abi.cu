@@ -14,11 +14,13 @@ int to_cfg4(const renv_dr_cfg *dr, DrCfg4 *out)
     out->dr_type = kDrNone;
     out->dim = 4;
     for (int k = 0; k < 4; ++k) { out->a[k] = 0.0; out->b[k] = 0.0; out->lb[k] = 0.0; }
+    for (int k = 0; k < 16; ++k) out->factor[k] = 0.0;
     if (dr == nullptr || dr->dr_type == RENV_DR_NONE) return RENV_OK;
-    if (dr->dr_type < RENV_DR_NONE || dr->dr_type > RENV_DR_GAUSSIAN) return RENV_E_DRTYPE;
+    if (dr->dr_type < RENV_DR_NONE || dr->dr_type > RENV_DR_FULLGAUSSIAN) return RENV_E_DRTYPE;
     if (dr->dim != 4) return RENV_E_DIM;
     out->dr_type = dr->dr_type;
     for (int k = 0; k < 4; ++k) { out->a[k] = dr->a[k]; out->b[k] = dr->b[k]; out->lb[k] = dr->lb[k]; }
+    for (int k = 0; k < 16; ++k) out->factor[k] = dr->dr_type == RENV_DR_FULLGAUSSIAN ? dr->factor[k] : 0.0;
     return RENV_OK;
 }
 
@@ -53,8 +55,21 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
     if (out == nullptr || cfg == nullptr) return RENV_E_NULL;
     if (n <= 0) return RENV_E_SIZE;
     if (cfg->dim < 1 || cfg->dim > RENV_MAX_DIM) return RENV_E_DIM;
-    if (cfg->dr_type < RENV_DR_UNIFORM || cfg->dr_type > RENV_DR_GAUSSIAN) return RENV_E_DRTYPE;
+    if (cfg->dr_type < RENV_DR_UNIFORM || cfg->dr_type > RENV_DR_FULLGAUSSIAN) return RENV_E_DRTYPE;
     if (!aligned(out, 16)) return RENV_E_ALIGN;
+    if (cfg->dr_type == RENV_DR_FULLGAUSSIAN) {
+        FullGaussCfg<T> g;
+        g.dim = cfg->dim;
+        for (int k = 0; k < 32; ++k) { g.mean[k] = (T)cfg->a[k]; g.lo[k] = (T)cfg->b[k]; g.hi[k] = (T)cfg->lb[k]; }
+        for (int k = 0; k < cfg->dim * cfg->dim; ++k) g.factor[k] = (T)cfg->factor[k];
+        for (int k = cfg->dim * cfg->dim; k < 32 * 32; ++k) g.factor[k] = T(0);
+        constexpr int kTileG = fullgauss_tile<T>();
+        const int64_t gblocks = (n + kTileG - 1) / kTileG;
+        if (gblocks > 0x7fffffffLL) return RENV_E_SIZE;
+        dr_sample_fullgaussian_kernel<T><<<(unsigned)gblocks, kSampleThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            out, n, g, seed, sample_id0, call);
+        return launch_status();
+    }
     DrCfgFull c;
     c.dr_type = cfg->dr_type;
     c.dim = cfg->dim;

@@ -184,14 +184,37 @@ __device__ __forceinline__ void init_state(State<double> &s, uint64_t seed, uint
     s.theta_dot = __dadd_rn(-0.05, __dmul_rn(0.1, v[1]));
 }
 
+// fullgaussian for the 4-dim cart-pole xi: x = mean + F z in the normalised space, clip, denormalise.
+// Deliberately NOT inlined: it is the rarest branch of the (already cold) reset path and inlining it costs the
+// fused rollout kernel 40 registers.  `cfg` points into the kernel's __grid_constant__ parameter block.
+template <typename T>
+__device__ __noinline__ void fullgaussian_xi(const DrCfg4 *cfg, uint64_t seed, uint64_t id, uint64_t tick, T *v)
+{
+    constexpr int P = Pack<T>::kPerBlock;
+    T z[4];
+#pragma unroll
+    for (int j = 0; j < 4 / P; ++j) Num<T>::normals(draw_block(seed, id, tick, kXi, (uint32_t)j), z + j * P);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        T x = (T)cfg->a[d];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x = Num<T>::affine((T)cfg->factor[d * 4 + k], z[k], x);
+        v[d] = denormalize(x, (T)cfg->b[d], (T)cfg->lb[d]);
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ unsigned sample_xi(Xi<T> &p, const DrCfg4 &cfg, uint64_t seed, uint64_t id, uint64_t tick)
 {
     constexpr int P = Pack<T>::kPerBlock;
     T v[4] = { p.gravity, p.cart_mass, p.pole_mass, p.pole_length };
     unsigned violations = 0;
+    if (cfg.dr_type == kDrFullGaussian) {
+        fullgaussian_xi<T>(&cfg, seed, id, tick, v);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4 / P; ++j) violations += sample_dim_block<T>(cfg, seed, id, tick, kXi, j, v + j * P);
+        for (int j = 0; j < 4 / P; ++j) violations += sample_dim_block<T>(cfg, seed, id, tick, kXi, j, v + j * P);
+    }
     p.gravity = v[0]; p.cart_mass = v[1]; p.pole_mass = v[2]; p.pole_length = v[3];
     return violations;
 }

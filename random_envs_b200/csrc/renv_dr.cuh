@@ -22,13 +22,16 @@ constexpr double kPhiMinus2 = 0.022750131948179195;      // Phi(-2)
 constexpr double kPhiSpan = 0.9544997361036416;          // Phi(2) - Phi(-2)
 constexpr double kGaussianFloor = 0.1;                   // random_env.py:181 (hard-coded)
 
-enum DrType : int { kDrNone = 0, kDrUniform = 1, kDrTruncnorm = 2, kDrGaussian = 3 };
+enum DrType : int { kDrNone = 0, kDrUniform = 1, kDrTruncnorm = 2, kDrGaussian = 3, kDrFullGaussian = 4 };
 
 // Compact 4-dim image of renv_dr_cfg for the cart-pole kernels (passed by value as a kernel parameter).
+// fullgaussian (random_env.py:192-198): a = mean in the normalised [0,4] space, b / lb = search-bound lo / hi,
+// factor = any F with F F^T = cov (row-major 4x4).
 struct DrCfg4 {
     int dr_type;
     int dim;
     double a[4], b[4], lb[4];
+    double factor[16];
 };
 
 template <typename T> struct Num;
@@ -78,6 +81,19 @@ template <> struct Num<double> {
     __device__ static __forceinline__ void normals(uint4 r, double z[2]) { Pack<double>::normals(r, z); }
 };
 
+// fullgaussian tail (random_env.py:194-198 + denormalize_parameters :205-220): clip to [0, 4], then
+// (p * (hi - lo)) / 4 + lo in that operator order.
+__device__ __forceinline__ float denormalize(float x, float lo, float hi)
+{
+    x = fminf(fmaxf(x, 0.0f), 4.0f);
+    return fmaf(__fmul_rn(x, __fsub_rn(hi, lo)), 0.25f, lo);
+}
+__device__ __forceinline__ double denormalize(double x, double lo, double hi)
+{
+    x = fmin(fmax(x, 0.0), 4.0);
+    return __dadd_rn(__ddiv_rn(__dmul_rn(x, __dsub_rn(hi, lo)), 4.0), lo);
+}
+
 // Parameters of one dim block (dims j*P .. j*P+P-1) held in registers, already converted to T.
 template <typename T> struct DimBlock {
     static constexpr int P = Pack<T>::kPerBlock;
@@ -95,7 +111,8 @@ template <typename T, typename Cfg> __device__ __forceinline__ DimBlock<T> load_
         const int d = j * P + k;
         const bool ok = d < cfg.dim;
         blk.a[k] = ok ? (T)cfg.a[d] : T(0);
-        blk.b[k] = ok ? (T)cfg.b[d] : T(0);
+        // scale: hi - lo for uniform (rounded once, as numpy's `high - low`), std otherwise
+        blk.b[k] = ok ? (cfg.dr_type == kDrUniform ? Num<T>::sub((T)cfg.b[d], (T)cfg.a[d]) : (T)cfg.b[d]) : T(0);
         blk.floor[k] = ok ? (cfg.dr_type == kDrTruncnorm ? (T)cfg.lb[d] : (T)kGaussianFloor) : T(0);
         if (ok) blk.valid |= 1u << k;
     }
@@ -113,12 +130,30 @@ __device__ __forceinline__ unsigned sample_dim_block(int dr_type, const DimBlock
         T u[P];
         Pack<T>::uniforms(draw_block(seed, id, tick, purpose, (uint32_t)j), u);
 #pragma unroll
-        for (int k = 0; k < P; ++k)
-            if (blk.valid & (1u << k)) out[k] = Num<T>::affine(Num<T>::sub(blk.b[k], blk.a[k]), u[k], blk.a[k]);
+        for (int k = 0; k < P; ++k)      // dims beyond `dim` have a = b = 0 and are never stored by the caller
+            out[k] = Num<T>::affine(blk.b[k], u[k], blk.a[k]);
     } else if (dr_type == kDrTruncnorm || dr_type == kDrGaussian) {
         const bool tn = dr_type == kDrTruncnorm;
-        unsigned pending = blk.valid;
-        for (int t = 0; t < 3 && pending; ++t) {
+        // attempt 0 for the whole block, branch-free: almost always every dim is accepted and we are done
+        unsigned pending = 0;
+        {
+            const uint4 r = draw_block(seed, id, tick, purpose, (uint32_t)j);
+            T z[P];
+            if (tn) {
+                Pack<T>::uniforms(r, z);
+#pragma unroll
+                for (int k = 0; k < P; ++k) z[k] = Num<T>::tn_z(z[k]);
+            } else {
+                Num<T>::normals(r, z);
+            }
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                out[k] = Num<T>::affine(blk.b[k], z[k], blk.a[k]);
+                if (out[k] < blk.floor[k]) pending |= 1u << k;      // the reference's loop condition: `obs < bound`
+            }
+            pending &= blk.valid;
+        }
+        for (int t = 1; t < 3 && pending; ++t) {                    // redraws, only for the rejected dims
             const uint4 r = draw_block(seed, id, tick, purpose, (uint32_t)(t * 16 + j));
             T z[P];
             if (tn) {
@@ -132,7 +167,7 @@ __device__ __forceinline__ unsigned sample_dim_block(int dr_type, const DimBlock
             for (int k = 0; k < P; ++k) {
                 if (pending & (1u << k)) {
                     const T x = Num<T>::affine(blk.b[k], z[k], blk.a[k]);
-                    if (!(x < blk.floor[k])) {        // the reference's loop condition is `obs < bound`
+                    if (!(x < blk.floor[k])) {
                         out[k] = x;
                         pending &= ~(1u << k);
                     }

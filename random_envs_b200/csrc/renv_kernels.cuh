@@ -85,7 +85,7 @@ constexpr int kStepThreads = 256;
 // CTA-local indices are appended to a shared-memory list and, after one __syncthreads, the first `count`
 // threads of the CTA each reset one env at full lane utilisation, overwriting the owner's stores.
 template <typename T, bool kAutoReset>
-__global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 2)) cartpole_step_kernel(const StepArgs<T> a)
+__global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpole_step_kernel(const __grid_constant__ StepArgs<T> a)
 {
     using VT = VecTraits<T>;
     constexpr int V = VT::V;
@@ -196,7 +196,7 @@ template <typename T> struct ResetArgs {
     unsigned long long *violations;
 };
 
-template <typename T> __global__ void __launch_bounds__(256) cartpole_reset_kernel(const ResetArgs<T> a)
+template <typename T> __global__ void __launch_bounds__(256) cartpole_reset_kernel(const __grid_constant__ ResetArgs<T> a)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.env.n) return;
@@ -280,7 +280,8 @@ __device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); retu
 __device__ __forceinline__ double pin(double v) { asm volatile("" : "+d"(v)); return v; }
 
 template <typename T, bool kEuler>
-__global__ void __launch_bounds__(kRolloutThreads) cartpole_rollout_kernel(const RolloutArgs<T> a)
+__global__ void __launch_bounds__(kRolloutThreads, (sizeof(T) == 4 ? 3 : 2))
+cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ld = a.env.ld;
@@ -414,6 +415,61 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
     for (int q = threadIdx.x; q < nvec; q += blockDim.x)
         reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(tile)[q];
     for (int q = nvec * W + threadIdx.x; q < total; q += blockDim.x) dst[q] = tile[q];
+}
+
+// ------------------------------------------------------------------------------------------------
+// sample_tasks(n) for dr_type 'fullgaussian' (random_env.py:192-198): x = mean + F z, clip [0,4], denormalise
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct FullGaussCfg {
+    int dim;
+    T mean[32], lo[32], hi[32];
+    T factor[32 * 32];           // row-major F, F F^T = cov  (4.4 KB fp32 / 8.8 KB fp64: a large kernel parameter)
+};
+template <typename T> __host__ __device__ constexpr int fullgauss_tile() { return 512 / (int)sizeof(T); }   // 128 / 64 rows
+
+template <typename T>
+__global__ void __launch_bounds__(kSampleThreads) dr_sample_fullgaussian_kernel(T *__restrict__ out, int64_t n,
+                                                                                const __grid_constant__ FullGaussCfg<T> cfg,
+                                                                                uint64_t seed, uint64_t sample_id0,
+                                                                                uint32_t call)
+{
+    constexpr int P = Pack<T>::kPerBlock;
+    constexpr int kTile = fullgauss_tile<T>();
+    __shared__ __align__(16) T zt[kTile * 32];
+    __shared__ __align__(16) T xt[kTile * 32];
+    __shared__ T fs[32 * 32];    // the factor, staged once: per-lane rows would serialise on the constant bank
+    const int dim = cfg.dim;
+    for (int q = threadIdx.x; q < dim * dim; q += blockDim.x) fs[q] = cfg.factor[q];
+    const int blocks_per_sample = (dim + P - 1) / P;
+    const int64_t first = (int64_t)blockIdx.x * kTile;
+    const int samples = (int)min((int64_t)kTile, n - first);
+    // phase 1: standard normals, one Philox block per (sample, dim block)
+    for (int it = threadIdx.x; it < samples * blocks_per_sample; it += blockDim.x) {
+        const int sidx = it / blocks_per_sample, j = it - sidx * blocks_per_sample;
+        T z[P];
+        Num<T>::normals(draw_block(seed, sample_id0 + (uint64_t)(first + sidx), call, kTasks, (uint32_t)j), z);
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+            if (j * P + k < dim) zt[sidx * dim + j * P + k] = z[k];
+    }
+    __syncthreads();
+    // phase 2: one output element per thread-iteration: dim FMAs against the factor row
+    for (int e = threadIdx.x; e < samples * dim; e += blockDim.x) {
+        const int sidx = e / dim, d = e - sidx * dim;
+        T x = cfg.mean[d];
+        const T *zr = zt + sidx * dim;
+        const T *fr = fs + d * dim;
+        for (int k = 0; k < dim; ++k) x = Num<T>::affine(fr[k], zr[k], x);
+        xt[e] = denormalize(x, cfg.lo[d], cfg.hi[d]);
+    }
+    __syncthreads();
+    const int total = samples * dim;
+    T *dst = out + first * dim;
+    constexpr int W = 16 / sizeof(T);
+    const int nvec = total / W;
+    for (int q = threadIdx.x; q < nvec; q += blockDim.x)
+        reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(xt)[q];
+    for (int q = nvec * W + threadIdx.x; q < total; q += blockDim.x) dst[q] = xt[q];
 }
 
 // ------------------------------------------------------------------------------------------------

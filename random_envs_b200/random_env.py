@@ -24,6 +24,19 @@ SAMPLING_UNSET_MSG = ("sampling value of random env needs to be set before using
 GAUSSIAN_FAIL_MSG = "Not all samples were above > 0.1 after 2 attempts"
 
 
+def covariance_factor(cov):
+    """A matrix F with F F^T = cov.  numpy's multivariate_normal (random_env.py:194) factors cov by SVD; any factor
+    gives the same law.  Cholesky when cov is positive definite, symmetric eigen-decomposition otherwise (PSD)."""
+    cov = np.asarray(cov, dtype=np.float64)
+    if cov.ndim != 2 or cov.shape[0] != cov.shape[1]:
+        raise ValueError("cov must be a square matrix")
+    try:
+        return np.linalg.cholesky(cov)
+    except np.linalg.LinAlgError:
+        w, v = np.linalg.eigh((cov + cov.T) / 2)
+        return v * np.sqrt(np.clip(w, 0.0, None))
+
+
 class RandomEnv(Env):
     """Superclass for all environments supporting Domain Randomization of dynamics parameters."""
 
@@ -107,13 +120,18 @@ class RandomEnv(Env):
             raise ValueError("Not implemented")
         return None
 
+    def _task_len(self):
+        # the reference uses len(self.get_task()); a vector env's get_task() is (N, task_dim), so prefer task_dim
+        dim = getattr(self, "task_dim", None)
+        return int(dim) if dim else len(self.get_task())
+
     def set_task_search_bounds(self):
-        for i in range(len(self.get_task())):
+        for i in range(self._task_len()):
             self.min_task[i], self.max_task[i] = self.get_search_bounds_mean(i)
         self._on_distribution_change()
 
     def get_task_search_bounds(self):
-        dim = len(self.get_task())
+        dim = self._task_len()
         bounds = np.array([self.get_search_bounds_mean(i) for i in range(dim)], dtype=float).reshape(dim, 2)
         return bounds[:, 0].copy(), bounds[:, 1].copy()
 
@@ -144,8 +162,11 @@ class RandomEnv(Env):
             a, b = self.min_task, self.max_task
         elif self.sampling in ("truncnorm", "gaussian"):
             a, b = self.mean_task, self.stdev_task
+        elif self.sampling == "fullgaussian":
+            lo, hi = self.get_task_search_bounds()
+            return _lib.make_dr_cfg("fullgaussian", self.mean_task, lo, hi, covariance_factor(self.cov_task))
         else:
-            raise NotImplementedError("dr_type %r is not implemented on the device yet" % self.sampling)
+            raise Exception("Unknown dr_type:" + str(self.sampling))
         lb = [self.get_task_lower_bound(i) for i in range(len(a))] if self.sampling == "truncnorm" else None
         return _lib.make_dr_cfg(self.sampling, a, b, lb)
 

@@ -119,3 +119,34 @@ def test_live_reference_30dim_humanoid_table():
     env.set_dr_distribution("nope", []) if False else None
     with pytest.raises(Exception, match="Unknown dr_type:nope"):
         env.set_dr_distribution("nope", [])
+
+
+def test_fullgaussian_port_describes_the_references_draws(golden_dir):
+    """denormalize(clip(mean + F z)) with F F^T = cov has the law of the reference's fullgaussian sample_task."""
+    from random_envs_b200.random_env import covariance_factor
+    g = np.load(os.path.join(golden_dir, "sampler_reference_draws.npz"))
+    mean, cov, ref = g["fullgaussian_mean"], g["fullgaussian_cov"], g["fullgaussian"]
+    lo, hi = np.array([2.0, 0.5, 0.05, 0.1]), np.array([20.0, 3.0, 0.3, 1.0])     # random_cartpole.py:127-132
+    f = covariance_factor(cov)
+    assert np.allclose(f @ f.T, cov, atol=1e-14)
+    z = np.random.RandomState(3).randn(200000, 4)
+    x = dr_port.sample_fullgaussian_from_z(mean, f, lo, hi, z)
+    assert np.all(x >= lo) and np.all(x <= hi)
+    for d in range(4):
+        assert stats.ks_2samp(x[:, d], ref[:, d]).pvalue > 1e-3, d
+    # clipping on both sides of dim 3 shows up as atoms at the search bounds, in the port and in the reference
+    for v in (lo[3], hi[3]):
+        assert abs(np.mean(x[:, 3] == v) - np.mean(ref[:, 3] == v)) < 0.02 and np.mean(ref[:, 3] == v) > 0.02
+    assert np.max(np.abs(np.corrcoef(x.T) - np.corrcoef(ref.T))) < 0.05
+    # singular covariance still factors (eigen fallback)
+    s = np.array([[1.0, 1.0], [1.0, 1.0]])
+    fs = covariance_factor(s)
+    assert np.allclose(fs @ fs.T, s, atol=1e-12)
+
+
+@needs_ref
+def test_fullgaussian_port_vs_live_reference_denormalisation():
+    env = rl.make_cartpole()
+    p = np.array([0.0, 4.0, 2.0, 1.0])
+    lo, hi = env.get_task_search_bounds()
+    assert np.array_equal(env.denormalize_parameters(p), dr_port.denormalize(p, lo, hi))
