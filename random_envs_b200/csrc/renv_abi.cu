@@ -77,8 +77,7 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
     constexpr int kTile = tile_samples<T>();
     const int64_t blocks = (n + kTile - 1) / kTile;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
-    const size_t smem = (size_t)kTile * cfg->dim * sizeof(T);     // <= 32 KB
-    dr_sample_kernel<T><<<(unsigned)blocks, kSampleThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+    dr_sample_kernel<T><<<(unsigned)blocks, kSampleThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         out, n, c, seed, sample_id0, call, violations);
     return launch_status();
 }

@@ -369,20 +369,46 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 // the tile is written back with fully coalesced 128-bit stores whatever `dim` is (30 is not a
 // multiple of 4: a thread-per-sample store would touch 32 sectors per instruction).
 constexpr int kSampleThreads = 256;
-template <typename T> __host__ __device__ constexpr int tile_samples() { return 1024 / (int)sizeof(T); }   // 256 float / 128 double rows
+template <typename T> __host__ __device__ constexpr int tile_samples() { return 1024 / (int)sizeof(T); }   // samples per CTA: 256 float / 128 double
 
 struct DrCfgFull { int dr_type; int dim; double a[32]; double b[32]; double lb[32]; };
 
-// Thread t owns dim block j = t % jpad (jpad = blocks per sample rounded up to a power of two) for the whole
-// kernel, so its distribution parameters are read and converted ONCE into registers and the sample loop is
-// Philox + transform + 4 shared-memory stores, with shifts instead of divisions.
+// Work item = (sample, dim block of 4 floats / 2 doubles = one Philox call).  Thread t owns dim block
+// j = t % jpad (jpad = blocks per sample rounded up to a power of two) for the whole kernel, so its distribution
+// parameters are read and converted ONCE into registers and the sample loop is Philox + transform + store, with
+// shifts instead of divisions.  Consecutive lanes hold consecutive (sample, block) items = consecutive 16-byte
+// chunks of the row-major (n, dim) output, so each warp store instruction covers one contiguous span and no
+// shared-memory staging is needed; the store width follows the row alignment (dim % 4 == 0: 128-bit,
+// dim even: 64-bit pairs -- e.g. the 30-dim humanoid --, otherwise scalars).
+template <typename T> __device__ __forceinline__ void store_block(T *row, const T *v, unsigned valid, int dim);
+template <> __device__ __forceinline__ void store_block<float>(float *row, const float *v, unsigned valid, int dim)
+{
+    if ((dim & 3) == 0) {
+        *reinterpret_cast<float4 *>(row) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if ((dim & 1) == 0) {
+        if (valid & 1u) *reinterpret_cast<float2 *>(row) = make_float2(v[0], v[1]);
+        if (valid & 4u) *reinterpret_cast<float2 *>(row + 2) = make_float2(v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (valid & (1u << k)) row[k] = v[k];
+    }
+}
+template <> __device__ __forceinline__ void store_block<double>(double *row, const double *v, unsigned valid, int dim)
+{
+    if ((dim & 1) == 0) {
+        *reinterpret_cast<double2 *>(row) = make_double2(v[0], v[1]);
+    } else {
+        if (valid & 1u) row[0] = v[0];
+        if (valid & 2u) row[1] = v[1];
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict__ out, int64_t n, const DrCfgFull cfg,
                                                                    uint64_t seed, uint64_t sample_id0, uint32_t call,
                                                                    unsigned long long *violations)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *tile = reinterpret_cast<T *>(smem_raw);
     constexpr int P = Pack<T>::kPerBlock;
     constexpr int kTile = tile_samples<T>();
     const int dim = cfg.dim;
@@ -393,28 +419,19 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
     const int lane_sample = threadIdx.x >> log2pad, samples_per_pass = kSampleThreads >> log2pad;
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int samples = (int)min((int64_t)kTile, n - first);
+    if (j >= blocks_per_sample) return;
+    const DimBlock<T> blk = load_dim_block<T>(cfg, j);
+    const int dr_type = cfg.dr_type;
     unsigned viol = 0;
-    if (j < blocks_per_sample) {
-        const DimBlock<T> blk = load_dim_block<T>(cfg, j);
-        const int dr_type = cfg.dr_type;
-        for (int sidx = lane_sample; sidx < samples; sidx += samples_per_pass) {
-            T v[P];
-            viol += sample_dim_block<T>(dr_type, blk, seed, sample_id0 + (uint64_t)(first + sidx), call, kTasks, j, v);
-            T *row = tile + sidx * dim + j * P;
-#pragma unroll
-            for (int k = 0; k < P; ++k)
-                if (blk.valid & (1u << k)) row[k] = v[k];
-        }
+    T *row = out + (first + lane_sample) * dim + j * P;
+    const int64_t row_step = (int64_t)samples_per_pass * dim;
+    uint64_t id = sample_id0 + (uint64_t)(first + lane_sample);
+    for (int sidx = lane_sample; sidx < samples; sidx += samples_per_pass, row += row_step, id += samples_per_pass) {
+        T v[P];
+        viol += sample_dim_block<T>(dr_type, blk, seed, id, call, kTasks, j, v);
+        store_block<T>(row, v, blk.valid, dim);
     }
     if (viol && violations) atomicAdd(violations, (unsigned long long)viol);
-    __syncthreads();
-    const int total = samples * dim;
-    T *dst = out + first * dim;
-    constexpr int W = 16 / sizeof(T);
-    const int nvec = total / W;
-    for (int q = threadIdx.x; q < nvec; q += blockDim.x)
-        reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(tile)[q];
-    for (int q = nvec * W + threadIdx.x; q < total; q += blockDim.x) dst[q] = tile[q];
 }
 
 // ------------------------------------------------------------------------------------------------
