@@ -14,9 +14,10 @@
  *   - Return value: 0 = OK; < 0 = invalid argument (enum renv_status); > 0 = cudaError_t of the launch.
  *   - Alignment: `state`, `xi`, `reward`, `elapsed`, `out` 16 bytes; `action`, `done`, `truncated`,
  *     `mask` 4 bytes; `ld` a multiple of 4 (f32) or 2 (f64).  Violations return RENV_E_ALIGN.
- *   - Layout: structure-of-arrays.  `state` is (4, ld): rows x, x_dot, theta, theta_dot;
- *     `xi` is (4, ld): rows gravity, cart_mass, pole_mass, pole_length
- *     (order of random_envs/random_cartpole.py:104-107,149-155).
+ *   - Layout: `state` is structure-of-arrays (4, ld): rows x, x_dot, theta, theta_dot.  `xi` is one row per env,
+ *     (n, 4) row-major: columns gravity, cart_mass, pole_mass, pole_length (order of
+ *     random_envs/random_cartpole.py:104-107,149-155) -- the layout of get_task() / sample_tasks(n), and a reset
+ *     rewrites one 32-byte sector instead of four.
  *   - RNG: counter-based Philox4x32-10, key = seed, counter = (global env id, tick, purpose|slot).  `tick` is
  *     the caller's step clock (48 bits used): pass a value that grows by 1 per reset/step call and by K per
  *     K-step rollout (step k of a rollout uses tick + k).  An env starts at most one episode per tick, so
@@ -78,12 +79,12 @@ typedef struct renv_dr_cfg {
 /* One shard of cart-pole envs resident in HBM (device pointers, element type T = float | double). */
 typedef struct renv_cartpole_env {
     void *state;                 /* T (4, ld)   RandomCartPoleEnv.state            :176,198 */
-    void *xi;                    /* T (4, ld)   gravity, cart_mass, pole_mass, pole_length :157-166 */
+    void *xi;                    /* T (n, 4)    gravity, cart_mass, pole_mass, pole_length :157-166 */
     int32_t *elapsed;            /* (n) TimeLimit._elapsed_steps (gym 0.21)                 */
     uint32_t *episode;           /* (n) episodes started per env (statistics only; may be NULL)   */
     int32_t *beyond;             /* (n) steps_beyond_done, -1 == None (:207-222); may be NULL when auto_reset */
     int64_t n;                   /* envs in this shard */
-    int64_t ld;                  /* row stride of state/xi in elements, >= n */
+    int64_t ld;                  /* row stride of state in elements, >= n */
     uint64_t env_id0;            /* global id of env 0 of this shard (rank * n under contiguous sharding) */
     uint64_t seed;               /* Philox key */
 } renv_cartpole_env;

@@ -1,8 +1,8 @@
 // sm_100a kernels of the DR cart-pole hot path.  Launched only through the C ABI in renv_abi.cu.
 //
-// Memory design (HBM3e-bound single step): structure-of-arrays, one thread owns V consecutive envs
-// (V = 4 floats / 2 doubles = one 128-bit access per row), so every global access of the main path is
-// a fully coalesced LDG.E.128 / STG.E.128: per env-step 37 B read + 25 B written in fp32 (62 B),
+// Memory design (HBM3e-bound single step): structure-of-arrays state (4, ld), one row per env for xi
+// (n, 4); one thread owns V consecutive envs (V = 4 floats / 2 doubles = one 128-bit access per state
+// row and per xi row), so every global access of the main path is a 128-bit LDG.E.128 / STG.E.128: per env-step 37 B read + 25 B written in fp32 (62 B),
 // 69 + 45 = 114 B in fp64 (DESIGN.md "algorithmic bytes").  All loads are issued before the first
 // use (10 independent 128-bit requests per thread in flight).  Auto-reset and the DR resample are
 // fused into the same kernel: only envs that finished rewrite `xi`, and nothing is loaded for a reset
@@ -40,6 +40,29 @@ template <typename Vec, typename S, int V> __device__ __forceinline__ void vstor
     *reinterpret_cast<Vec *>(dst) = v;
 }
 
+// xi is array-of-rows, (n, 4) row-major: one 16-byte (float) / 32-byte (double) row per env, so that a reset
+// dirties ONE 32-byte DRAM sector instead of one in each of four SoA rows (ncu, 2^24 envs: +80 MB of write-backs
+// per step with SoA xi).  Reads stay sector-exact: a thread's V rows are contiguous and the warp's span is one block.
+__device__ __forceinline__ Xi<float> load_xi(const float *xi, int64_t i)
+{
+    const float4 v = *reinterpret_cast<const float4 *>(xi + 4 * i);
+    return Xi<float>{ v.x, v.y, v.z, v.w };
+}
+__device__ __forceinline__ Xi<double> load_xi(const double *xi, int64_t i)
+{
+    const double2 a = *reinterpret_cast<const double2 *>(xi + 4 * i), b = *reinterpret_cast<const double2 *>(xi + 4 * i + 2);
+    return Xi<double>{ a.x, a.y, b.x, b.y };
+}
+__device__ __forceinline__ void store_xi(float *xi, int64_t i, const Xi<float> &p)
+{
+    *reinterpret_cast<float4 *>(xi + 4 * i) = make_float4(p.gravity, p.cart_mass, p.pole_mass, p.pole_length);
+}
+__device__ __forceinline__ void store_xi(double *xi, int64_t i, const Xi<double> &p)
+{
+    *reinterpret_cast<double2 *>(xi + 4 * i) = make_double2(p.gravity, p.cart_mass);
+    *reinterpret_cast<double2 *>(xi + 4 * i + 2) = make_double2(p.pole_mass, p.pole_length);
+}
+
 template <typename T> struct EnvPtrs {
     T *state; T *xi; int32_t *elapsed; uint32_t *episode; int32_t *beyond;
     int64_t n, ld; uint64_t env_id0, seed;
@@ -59,8 +82,7 @@ __device__ __forceinline__ unsigned reset_env(const EnvPtrs<T> &env, const DrCfg
     if (dr.dr_type != kDrNone) {
         Xi<T> xi = { T(0), T(0), T(0), T(0) };
         viol = sample_xi(xi, dr, env.seed, id, tick);
-        env.xi[0 * ld + i] = xi.gravity; env.xi[1 * ld + i] = xi.cart_mass;
-        env.xi[2 * ld + i] = xi.pole_mass; env.xi[3 * ld + i] = xi.pole_length;
+        store_xi(env.xi, i, xi);
     }
     if (env.episode) atomicAdd(env.episode + i, 1u);      // optional episode count: fire-and-forget RED, no load stall
     return viol;
@@ -97,14 +119,15 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpo
     const bool live = i0 < n;
     const bool full = i0 + V <= n;
 
-    T s[4][V], p[4][V];
+    T s[4][V];
+    Xi<T> p[V];
     int32_t el[V];
     uint8_t act[V];
     if (full) {     // all ten 128-bit requests go out before anything waits (incl. the barrier below)
 #pragma unroll
         for (int c = 0; c < 4; ++c) vload<typename VT::Real>(s[c], a.env.state + c * ld + i0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) vload<typename VT::Real>(p[c], a.env.xi + c * ld + i0);
+        for (int v = 0; v < V; ++v) p[v] = load_xi(a.env.xi, i0 + v);
         vload<typename VT::Int>(el, a.env.elapsed + i0);
         vload<typename VT::Byte>(act, a.action + i0);
     }
@@ -119,10 +142,8 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpo
             for (int v = 0; v < V; ++v) {
                 const bool ok = i0 + v < n;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    s[c][v] = ok ? a.env.state[c * ld + i0 + v] : T(0);
-                    p[c][v] = ok ? a.env.xi[c * ld + i0 + v] : T(1);
-                }
+                for (int c = 0; c < 4; ++c) s[c][v] = ok ? a.env.state[c * ld + i0 + v] : T(0);
+                p[v] = ok ? load_xi(a.env.xi, i0 + v) : Xi<T>{ T(1), T(1), T(1), T(1) };
                 el[v] = ok ? a.env.elapsed[i0 + v] : 0;
                 act[v] = ok ? a.action[i0 + v] : 0;
             }
@@ -134,8 +155,7 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpo
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             State<T> st = { s[0][v], s[1][v], s[2][v], s[3][v] };
-            const Xi<T> xi = { p[0][v], p[1][v], p[2][v], p[3][v] };
-            const bool terminated = dynamics(st, xi, derive(xi), act[v], euler);
+            const bool terminated = dynamics(st, p[v], derive(p[v]), act[v], euler);
             s[0][v] = st.x; s[1][v] = st.x_dot; s[2][v] = st.theta; s[3][v] = st.theta_dot;
             el[v] += 1;                                                    // TimeLimit.step
             bool done = terminated, trunc = false;
@@ -295,7 +315,7 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 
     if (live) {
         t.s = State<T>{ a.env.state[i], a.env.state[ld + i], a.env.state[2 * ld + i], a.env.state[3 * ld + i] };
-        t.p = Xi<T>{ a.env.xi[i], a.env.xi[ld + i], a.env.xi[2 * ld + i], a.env.xi[3 * ld + i] };
+        t.p = load_xi(a.env.xi, i);
         t.d = derive(t.p);
         t.el = a.env.elapsed[i];
         t.new_episodes = 0; t.xi_dirty = false;
@@ -310,10 +330,7 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 
         a.env.state[i] = t.s.x; a.env.state[ld + i] = t.s.x_dot; a.env.state[2 * ld + i] = t.s.theta;
         a.env.state[3 * ld + i] = t.s.theta_dot;
-        if (t.xi_dirty) {
-            a.env.xi[i] = t.p.gravity; a.env.xi[ld + i] = t.p.cart_mass; a.env.xi[2 * ld + i] = t.p.pole_mass;
-            a.env.xi[3 * ld + i] = t.p.pole_length;
-        }
+        if (t.xi_dirty) store_xi(a.env.xi, i, t.p);
         a.env.elapsed[i] = t.el;
         if (a.env.episode && t.new_episodes) a.env.episode[i] += t.new_episodes;
     }

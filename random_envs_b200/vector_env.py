@@ -16,8 +16,9 @@ Same method names as the reference's single env (random_cartpole.py / random_env
 (README.md:9; random_env.py:37-39).  The returned tensors are views of the env's own buffers (the
 reference's ``obs`` likewise aliases ``state``): they are overwritten by the next call.
 
-Storage is structure-of-arrays ``(4, ld)`` so that the kernels read and write 128-bit coalesced
-vectors; ``obs``/``get_task`` expose the transposed ``(N, 4)`` view.
+State is stored structure-of-arrays ``(4, ld)`` so that the kernels read and write 128-bit coalesced
+vectors (``obs`` is the transposed ``(N, 4)`` view); xi is stored one row per env, ``(N, 4)``, which is
+what ``get_task`` returns.
 """
 import ctypes
 import math
@@ -105,7 +106,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         dt = self.torch_dtype
         b = dict(device=dev, ld=ld)
         b["state"] = t.zeros((4, ld), dtype=dt, device=dev)
-        b["xi"] = t.tensor(NOMINAL_TASK, dtype=dt, device=dev).reshape(4, 1).repeat(1, ld).contiguous()
+        b["xi"] = t.tensor(NOMINAL_TASK, dtype=dt, device=dev).reshape(1, 4).repeat(ld, 1).contiguous()   # (ld, 4) rows
         b["elapsed"] = t.zeros(ld, dtype=t.int32, device=dev)
         b["episode"] = t.zeros(ld, dtype=t.int32, device=dev)       # uint32 bit pattern
         b["beyond"] = t.full((ld,), -1, dtype=t.int32, device=dev)
@@ -253,7 +254,7 @@ class RandomCartPoleVecEnv(RandomEnv):
 
     # ---- tasks --------------------------------------------------------------------------------------
     def get_task(self):
-        return self._alloc()["xi"][:, :self.num_envs].t()
+        return self._alloc()["xi"][:self.num_envs]
 
     def set_task(self, *task):
         """set_task(Tensor(N, 4)) for per-env xi, or set_task(g, m_c, m_p, l) to broadcast one task."""
@@ -266,10 +267,10 @@ class RandomCartPoleVecEnv(RandomEnv):
                 xi = xi.reshape(1, 4).expand(n, 4)
             if xi.shape != (n, 4):
                 raise ValueError("set_task expects (N, 4) or 4 scalars")
-            b["xi"][:, :n].copy_(xi.t())
+            b["xi"][:n].copy_(xi)
         elif len(task) == 4:
-            b["xi"][:, :n].copy_(t.tensor([float(v) for v in task], dtype=self.torch_dtype,
-                                          device=b["device"]).reshape(4, 1).expand(4, n))
+            b["xi"][:n].copy_(t.tensor([float(v) for v in task], dtype=self.torch_dtype,
+                                       device=b["device"]).reshape(1, 4).expand(n, 4))
         else:
             raise ValueError("set_task expects (N, 4) or 4 scalars")
 
