@@ -236,4 +236,4 @@ def test_fp64_step_is_bit_identical_to_the_oracle_on_nearly_every_env():
     got = _np(obs)
     same = np.all(got == ref.T, axis=1)
     assert same.mean() >= 0.98, same.mean()
-    assert np.max(np.abs(got - ref.T) / np.maximum(np.abs(ref.T), 1e-3)) <= 1e-14
+    assert np.max(np.abs(got - ref.T)) <= 1e-13
