@@ -2,6 +2,11 @@
 // Stateless and re-entrant: nothing is allocated, cached or synchronised here.
 #include "../../include/renv.h"
 #include "renv_kernels.cuh"
+#include "renv_rollout_pair.cuh"
+
+#ifndef RENV_ROLLOUT_F32_PAIR
+#define RENV_ROLLOUT_F32_PAIR 1     // 0: one env per thread (scalar FFMA) for A/B timing
+#endif
 
 using namespace renv;
 
@@ -129,6 +134,32 @@ int cartpole_step(const renv_cartpole_env *env, const uint8_t *action, T *reward
     return launch_status();
 }
 
+// fp64: one env per thread.  fp32: an env PAIR per thread on the packed FFMA2 pipe (renv_rollout_pair.cuh).
+int launch_rollout(const RolloutArgs<double> &a, cudaStream_t stream)
+{
+    const int64_t blocks = (a.env.n + kRolloutThreads - 1) / kRolloutThreads;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    if (a.euler) cartpole_rollout_kernel<double, true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+    else cartpole_rollout_kernel<double, false><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+    return launch_status();
+}
+int launch_rollout(const RolloutArgs<float> &a, cudaStream_t stream)
+{
+#if RENV_ROLLOUT_F32_PAIR
+    const int64_t threads = (a.env.n + 1) / 2;
+    const int64_t blocks = (threads + kRolloutThreads - 1) / kRolloutThreads;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    if (a.euler) cartpole_rollout_pair_kernel<true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+    else cartpole_rollout_pair_kernel<false><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+#else
+    const int64_t blocks = (a.env.n + kRolloutThreads - 1) / kRolloutThreads;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    if (a.euler) cartpole_rollout_kernel<float, true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+    else cartpole_rollout_kernel<float, false><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+#endif
+    return launch_status();
+}
+
 template <typename T>
 int cartpole_rollout(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator, int max_steps,
                      uint64_t tick, const renv_dr_cfg *dr, double *stats, unsigned long long *violations, void *stream)
@@ -149,13 +180,7 @@ int cartpole_rollout(const renv_cartpole_env *env, const double w[4], double b, 
     a.tick = tick;
     a.stats = stats;
     a.violations = violations;
-    const int64_t blocks = (env->n + kRolloutThreads - 1) / kRolloutThreads;
-    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
-    if (a.euler)
-        cartpole_rollout_kernel<T, true><<<(unsigned)blocks, kRolloutThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-    else
-        cartpole_rollout_kernel<T, false><<<(unsigned)blocks, kRolloutThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-    return launch_status();
+    return launch_rollout(a, static_cast<cudaStream_t>(stream));
 }
 
 template <typename T> int fma_peak(T *out, int blocks, int threads, int iters, void *stream)

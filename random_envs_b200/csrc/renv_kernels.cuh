@@ -251,6 +251,53 @@ __device__ __forceinline__ void atomic_max_f64(double *addr, double v)
     }
 }
 
+constexpr int kRolloutThreads = 256;
+
+// Episode statistics of one launch: warp shuffle -> shared -> one set of atomics per CTA into the 6 doubles
+// [episodes, sum return, sum return^2, min, max, sum length] (the vector the ranks all-gather).
+__device__ __forceinline__ void rollout_publish(double *stats, unsigned long long *violations, unsigned episodes,
+                                                unsigned sum_len, unsigned sum_r_u, unsigned long long sum_r2_u,
+                                                float min_r, float max_r, unsigned viol)
+{
+    double sum_r = (double)sum_r_u, sum_r2 = (double)sum_r2_u;
+    double cnt = (double)episodes, len = (double)sum_len;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        len += __shfl_xor_sync(0xffffffffu, len, off);
+        sum_r += __shfl_xor_sync(0xffffffffu, sum_r, off);
+        sum_r2 += __shfl_xor_sync(0xffffffffu, sum_r2, off);
+        min_r = fminf(min_r, __shfl_xor_sync(0xffffffffu, min_r, off));
+        max_r = fmaxf(max_r, __shfl_xor_sync(0xffffffffu, max_r, off));
+        viol += __shfl_xor_sync(0xffffffffu, viol, off);
+    }
+    __shared__ double sh[kRolloutThreads / 32][4];
+    __shared__ float shm[kRolloutThreads / 32][2];
+    __shared__ unsigned shv[kRolloutThreads / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh[warp][0] = cnt; sh[warp][1] = sum_r; sh[warp][2] = sum_r2; sh[warp][3] = len;
+        shm[warp][0] = min_r; shm[warp][1] = max_r; shv[warp] = viol;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 1; w < nw; ++w) {
+            cnt += sh[w][0]; sum_r += sh[w][1]; sum_r2 += sh[w][2]; len += sh[w][3];
+            min_r = fminf(min_r, shm[w][0]); max_r = fmaxf(max_r, shm[w][1]); viol += shv[w];
+        }
+        if (cnt > 0.0) {
+            atomicAdd(stats + 0, cnt);
+            atomicAdd(stats + 1, sum_r);
+            atomicAdd(stats + 2, sum_r2);
+            atomic_min_f64(stats + 3, (double)min_r);
+            atomic_max_f64(stats + 4, (double)max_r);
+            atomicAdd(stats + 5, len);
+        }
+        if (viol && violations) atomicAdd(violations, (unsigned long long)viol);
+    }
+}
+
 template <typename T> struct RolloutArgs {
     EnvPtrs<T> env;
     Policy<T> policy;
@@ -260,8 +307,6 @@ template <typename T> struct RolloutArgs {
     double *stats;
     unsigned long long *violations;
 };
-
-constexpr int kRolloutThreads = 256;
 
 // One env-step of the rollout: policy -> dynamics -> TimeLimit -> (rare) end-of-episode bookkeeping.
 // The reset itself is DEFERRED: the lane parks (t.waiting) with the clock tick of the step that ended the
@@ -386,48 +431,7 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
         a.env.elapsed[i] = t.el;
         if (a.env.episode && t.new_episodes) a.env.episode[i] += t.new_episodes;
     }
-    double sum_r = (double)t.sum_r, sum_r2 = (double)t.sum_r2;
-    float min_r = t.min_r, max_r = t.max_r;
-    const unsigned episodes = t.episodes, sum_len = t.sum_len;
-    unsigned viol = t.viol;
-
-    // warp shuffle -> shared -> one set of atomics per CTA
-    double cnt = (double)episodes, len = (double)sum_len;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-        len += __shfl_xor_sync(0xffffffffu, len, off);
-        sum_r += __shfl_xor_sync(0xffffffffu, sum_r, off);
-        sum_r2 += __shfl_xor_sync(0xffffffffu, sum_r2, off);
-        min_r = fminf(min_r, __shfl_xor_sync(0xffffffffu, min_r, off));
-        max_r = fmaxf(max_r, __shfl_xor_sync(0xffffffffu, max_r, off));
-        viol += __shfl_xor_sync(0xffffffffu, viol, off);
-    }
-    __shared__ double sh[kRolloutThreads / 32][4];
-    __shared__ float shm[kRolloutThreads / 32][2];
-    __shared__ unsigned shv[kRolloutThreads / 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        sh[warp][0] = cnt; sh[warp][1] = sum_r; sh[warp][2] = sum_r2; sh[warp][3] = len;
-        shm[warp][0] = min_r; shm[warp][1] = max_r; shv[warp] = viol;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int nw = blockDim.x >> 5;
-        for (int w = 1; w < nw; ++w) {
-            cnt += sh[w][0]; sum_r += sh[w][1]; sum_r2 += sh[w][2]; len += sh[w][3];
-            min_r = fminf(min_r, shm[w][0]); max_r = fmaxf(max_r, shm[w][1]); viol += shv[w];
-        }
-        if (cnt > 0.0) {
-            atomicAdd(a.stats + 0, cnt);
-            atomicAdd(a.stats + 1, sum_r);
-            atomicAdd(a.stats + 2, sum_r2);
-            atomic_min_f64(a.stats + 3, (double)min_r);
-            atomic_max_f64(a.stats + 4, (double)max_r);
-            atomicAdd(a.stats + 5, len);
-        }
-        if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
-    }
+    rollout_publish(a.stats, a.violations, t.episodes, t.sum_len, t.sum_r, t.sum_r2, t.min_r, t.max_r, t.viol);
 }
 
 // ------------------------------------------------------------------------------------------------
