@@ -111,12 +111,85 @@ template <typename T, typename Cfg> __device__ __forceinline__ DimBlock<T> load_
         const int d = j * P + k;
         const bool ok = d < cfg.dim;
         blk.a[k] = ok ? (T)cfg.a[d] : T(0);
-        // scale: hi - lo for uniform (rounded once, as numpy's `high - low`), std otherwise
-        blk.b[k] = ok ? (cfg.dr_type == kDrUniform ? Num<T>::sub((T)cfg.b[d], (T)cfg.a[d]) : (T)cfg.b[d]) : T(0);
+        // scale: hi - lo for uniform (rounded once, as numpy's `high - low`; fp32: times 2^-24, see uniform_affine), std otherwise
+        blk.b[k] = ok ? (cfg.dr_type == kDrUniform ? Pack<T>::uniform_scale(Num<T>::sub((T)cfg.b[d], (T)cfg.a[d])) : (T)cfg.b[d]) : T(0);
         blk.floor[k] = ok ? (cfg.dr_type == kDrTruncnorm ? (T)cfg.lb[d] : (T)kGaussianFloor) : T(0);
         if (ok) blk.valid |= 1u << k;
     }
     return blk;
+}
+
+// One standard draw per dim of the block for attempt `t`: truncnorm -> TN(-2,2) by inverse CDF, gaussian -> N(0,1).
+template <typename T>
+__device__ __forceinline__ void standard_draws(bool tn, uint64_t seed, uint64_t id, uint64_t tick, uint32_t purpose,
+                                               uint32_t slot, T *z)
+{
+    constexpr int P = Pack<T>::kPerBlock;
+    const uint4 r = draw_block(seed, id, tick, purpose, slot);
+    if (tn) {
+        Pack<T>::uniforms(r, z);
+#pragma unroll
+        for (int k = 0; k < P; ++k) z[k] = Num<T>::tn_z(z[k]);
+    } else {
+        Num<T>::normals(r, z);
+    }
+}
+
+// Attempt 0 for the whole block, branch-free (the common case: every dim accepted).  Returns the mask of dims
+// whose draw fell below the floor and must be redrawn.  uniform: out is final, mask 0.
+template <typename T>
+__device__ __forceinline__ unsigned first_attempt(int dr_type, const DimBlock<T> &blk, uint64_t seed, uint64_t id,
+                                                  uint64_t tick, uint32_t purpose, int j, T *out)
+{
+    constexpr int P = Pack<T>::kPerBlock;
+    unsigned pending = 0;
+    if (dr_type == kDrUniform) {
+        // dims beyond `dim` have a = b = 0 and are never stored by the caller
+        Pack<T>::uniform_affine(draw_block(seed, id, tick, purpose, (uint32_t)j), blk.b, blk.a, out);
+    } else if (dr_type == kDrTruncnorm || dr_type == kDrGaussian) {
+        T z[P];
+        standard_draws<T>(dr_type == kDrTruncnorm, seed, id, tick, purpose, (uint32_t)j, z);
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            out[k] = Num<T>::affine(blk.b[k], z[k], blk.a[k]);
+            if (out[k] < blk.floor[k]) pending |= 1u << k;      // the reference's loop condition: `obs < bound`
+        }
+        pending &= blk.valid;
+    }
+    return pending;
+}
+
+// Redraws (attempts 1 and 2) for the rejected dims only, then the reference's give-up rule.  Returns the number
+// of gaussian violations.
+template <typename T>
+__device__ __forceinline__ unsigned redraws(int dr_type, const DimBlock<T> &blk, uint64_t seed, uint64_t id,
+                                            uint64_t tick, uint32_t purpose, int j, unsigned pending, T *out)
+{
+    constexpr int P = Pack<T>::kPerBlock;
+    const bool tn = dr_type == kDrTruncnorm;
+    unsigned violations = 0;
+    for (int t = 1; t < 3 && pending; ++t) {
+        T z[P];
+        standard_draws<T>(tn, seed, id, tick, purpose, (uint32_t)(t * 16 + j), z);
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            if (pending & (1u << k)) {
+                const T x = Num<T>::affine(blk.b[k], z[k], blk.a[k]);
+                if (!(x < blk.floor[k])) {
+                    out[k] = x;
+                    pending &= ~(1u << k);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        if (pending & (1u << k)) {
+            out[k] = blk.floor[k];
+            if (!tn) ++violations;
+        }
+    }
+    return violations;
 }
 
 // Fills out[k] for the valid dims of the block.  Returns the number of gaussian violations.
@@ -124,65 +197,8 @@ template <typename T>
 __device__ __forceinline__ unsigned sample_dim_block(int dr_type, const DimBlock<T> &blk, uint64_t seed, uint64_t id,
                                                      uint64_t tick, uint32_t purpose, int j, T *out)
 {
-    constexpr int P = Pack<T>::kPerBlock;
-    unsigned violations = 0;
-    if (dr_type == kDrUniform) {
-        T u[P];
-        Pack<T>::uniforms(draw_block(seed, id, tick, purpose, (uint32_t)j), u);
-#pragma unroll
-        for (int k = 0; k < P; ++k)      // dims beyond `dim` have a = b = 0 and are never stored by the caller
-            out[k] = Num<T>::affine(blk.b[k], u[k], blk.a[k]);
-    } else if (dr_type == kDrTruncnorm || dr_type == kDrGaussian) {
-        const bool tn = dr_type == kDrTruncnorm;
-        // attempt 0 for the whole block, branch-free: almost always every dim is accepted and we are done
-        unsigned pending = 0;
-        {
-            const uint4 r = draw_block(seed, id, tick, purpose, (uint32_t)j);
-            T z[P];
-            if (tn) {
-                Pack<T>::uniforms(r, z);
-#pragma unroll
-                for (int k = 0; k < P; ++k) z[k] = Num<T>::tn_z(z[k]);
-            } else {
-                Num<T>::normals(r, z);
-            }
-#pragma unroll
-            for (int k = 0; k < P; ++k) {
-                out[k] = Num<T>::affine(blk.b[k], z[k], blk.a[k]);
-                if (out[k] < blk.floor[k]) pending |= 1u << k;      // the reference's loop condition: `obs < bound`
-            }
-            pending &= blk.valid;
-        }
-        for (int t = 1; t < 3 && pending; ++t) {                    // redraws, only for the rejected dims
-            const uint4 r = draw_block(seed, id, tick, purpose, (uint32_t)(t * 16 + j));
-            T z[P];
-            if (tn) {
-                Pack<T>::uniforms(r, z);
-#pragma unroll
-                for (int k = 0; k < P; ++k) z[k] = Num<T>::tn_z(z[k]);
-            } else {
-                Num<T>::normals(r, z);
-            }
-#pragma unroll
-            for (int k = 0; k < P; ++k) {
-                if (pending & (1u << k)) {
-                    const T x = Num<T>::affine(blk.b[k], z[k], blk.a[k]);
-                    if (!(x < blk.floor[k])) {
-                        out[k] = x;
-                        pending &= ~(1u << k);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-            if (pending & (1u << k)) {
-                out[k] = blk.floor[k];
-                if (!tn) ++violations;
-            }
-        }
-    }
-    return violations;
+    const unsigned pending = first_attempt<T>(dr_type, blk, seed, id, tick, purpose, j, out);
+    return pending ? redraws<T>(dr_type, blk, seed, id, tick, purpose, j, pending, out) : 0u;
 }
 
 template <typename T, typename Cfg>

@@ -441,8 +441,21 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 // doubles = one Philox call); values go to a shared-memory tile that is contiguous in the output, so
 // the tile is written back with fully coalesced 128-bit stores whatever `dim` is (30 is not a
 // multiple of 4: a thread-per-sample store would touch 32 sectors per instruction).
+#ifndef RENV_SAMPLER_ILP2
+#define RENV_SAMPLER_ILP2 0
+#endif
 constexpr int kSampleThreads = 256;
-template <typename T> __host__ __device__ constexpr int tile_samples() { return 1024 / (int)sizeof(T); }   // samples per CTA: 256 float / 128 double
+// Samples per CTA: every thread produces kItemsPerThread work items whatever `dim` is (dim 30: 256 float / 128 double
+// samples; dim 4: 2048 / 1024), so the per-thread set-up (12 parameter conversions) is amortised for the 3..4-dim
+// envs too.  Host and device use the same formula.
+constexpr int kItemsPerThread = 8;
+template <typename T> __host__ __device__ inline int tile_samples(int dim)
+{
+    const int blocks_per_sample = (dim + (int)(16 / sizeof(T)) - 1) / (int)(16 / sizeof(T));
+    int log2pad = 0;
+    while ((1 << log2pad) < blocks_per_sample) ++log2pad;
+    return (kSampleThreads * kItemsPerThread) >> log2pad;
+}
 
 struct DrCfgFull { int dr_type; int dim; double a[32]; double b[32]; double lb[32]; };
 
@@ -453,38 +466,47 @@ struct DrCfgFull { int dr_type; int dim; double a[32]; double b[32]; double lb[3
 // chunks of the row-major (n, dim) output, so each warp store instruction covers one contiguous span and no
 // shared-memory staging is needed; the store width follows the row alignment (dim % 4 == 0: 128-bit,
 // dim even: 64-bit pairs -- e.g. the 30-dim humanoid --, otherwise scalars).
-template <typename T> __device__ __forceinline__ void store_block(T *row, const T *v, unsigned valid, int dim);
-template <> __device__ __forceinline__ void store_block<float>(float *row, const float *v, unsigned valid, int dim)
+// kStore: 0 = one 128-bit store per block (float: dim % 4 == 0, double: dim even), 1 = float pairs (dim even),
+// 2 = scalars.  A template parameter like kDrType: a per-item `switch` on kernel parameters costs an LDC with a
+// ~40-cycle scoreboard wait in front of every Philox chain (ncu: short_scoreboard was the top stall).
+template <typename T, int kStore> __device__ __forceinline__ void store_block(T *row, const T *v, unsigned valid);
+template <> __device__ __forceinline__ void store_block<float, 0>(float *row, const float *v, unsigned)
 {
-    if ((dim & 3) == 0) {
-        *reinterpret_cast<float4 *>(row) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if ((dim & 1) == 0) {
-        if (valid & 1u) *reinterpret_cast<float2 *>(row) = make_float2(v[0], v[1]);
-        if (valid & 4u) *reinterpret_cast<float2 *>(row + 2) = make_float2(v[2], v[3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (valid & (1u << k)) row[k] = v[k];
-    }
+    *reinterpret_cast<float4 *>(row) = make_float4(v[0], v[1], v[2], v[3]);
 }
-template <> __device__ __forceinline__ void store_block<double>(double *row, const double *v, unsigned valid, int dim)
+template <> __device__ __forceinline__ void store_block<float, 1>(float *row, const float *v, unsigned valid)
 {
-    if ((dim & 1) == 0) {
-        *reinterpret_cast<double2 *>(row) = make_double2(v[0], v[1]);
-    } else {
-        if (valid & 1u) row[0] = v[0];
-        if (valid & 2u) row[1] = v[1];
-    }
+    *reinterpret_cast<float2 *>(row) = make_float2(v[0], v[1]);
+    if (valid & 4u) *reinterpret_cast<float2 *>(row + 2) = make_float2(v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store_block<float, 2>(float *row, const float *v, unsigned valid)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (valid & (1u << k)) row[k] = v[k];
+}
+template <> __device__ __forceinline__ void store_block<double, 0>(double *row, const double *v, unsigned)
+{
+    *reinterpret_cast<double2 *>(row) = make_double2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void store_block<double, 2>(double *row, const double *v, unsigned valid)
+{
+    row[0] = v[0];
+    if (valid & 2u) row[1] = v[1];
+}
+template <> __device__ __forceinline__ void store_block<double, 1>(double *row, const double *v, unsigned valid)
+{
+    store_block<double, 2>(row, v, valid);
 }
 
-template <typename T>
+template <typename T, int kDrType, int kStore>
 __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict__ out, int64_t n, const DrCfgFull cfg,
                                                                    uint64_t seed, uint64_t sample_id0, uint32_t call,
                                                                    unsigned long long *violations)
 {
     constexpr int P = Pack<T>::kPerBlock;
-    constexpr int kTile = tile_samples<T>();
     const int dim = cfg.dim;
+    const int kTile = tile_samples<T>(dim);
     const int blocks_per_sample = (dim + P - 1) / P;
     int log2pad = 0;
     while ((1 << log2pad) < blocks_per_sample) ++log2pad;
@@ -494,17 +516,33 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
     const int samples = (int)min((int64_t)kTile, n - first);
     if (j >= blocks_per_sample) return;
     const DimBlock<T> blk = load_dim_block<T>(cfg, j);
-    const int dr_type = cfg.dr_type;
     unsigned viol = 0;
-    T *row = out + (first + lane_sample) * dim + j * P;
-    const int64_t row_step = (int64_t)samples_per_pass * dim;
-    uint64_t id = sample_id0 + (uint64_t)(first + lane_sample);
-    for (int sidx = lane_sample; sidx < samples; sidx += samples_per_pass, row += row_step, id += samples_per_pass) {
-        T v[P];
-        viol += sample_dim_block<T>(dr_type, blk, seed, id, call, kTasks, j, v);
-        store_block<T>(row, v, blk.valid, dim);
+    T *const tile = out + (first + lane_sample) * dim + j * P;      // 64-bit once; 32-bit offsets inside the tile
+    const int row_step = samples_per_pass * dim;
+    const uint64_t id0 = sample_id0 + (uint64_t)(first + lane_sample);
+    // first block of the last (possibly shorter) row: its valid mask drops the dims beyond `dim`
+    int sidx = lane_sample, off = 0;
+#if RENV_SAMPLER_ILP2
+    // two independent Philox chains per iteration (a block is a ~100-cycle dependent IMAD.WIDE -> LOP3 chain)
+    for (; sidx + samples_per_pass < samples; sidx += 2 * samples_per_pass, off += 2 * row_step) {
+        T v0[P], v1[P];
+        const uint64_t id = id0 + (uint32_t)(sidx - lane_sample), id1 = id + (uint32_t)samples_per_pass;
+        const unsigned pend0 = first_attempt<T>(kDrType, blk, seed, id, call, kTasks, j, v0);
+        const unsigned pend1 = first_attempt<T>(kDrType, blk, seed, id1, call, kTasks, j, v1);
+        if (kDrType != kDrUniform && pend0) viol += redraws<T>(kDrType, blk, seed, id, call, kTasks, j, pend0, v0);
+        if (kDrType != kDrUniform && pend1) viol += redraws<T>(kDrType, blk, seed, id1, call, kTasks, j, pend1, v1);
+        store_block<T, kStore>(tile + off, v0, blk.valid);
+        store_block<T, kStore>(tile + off + row_step, v1, blk.valid);
     }
-    if (viol && violations) atomicAdd(violations, (unsigned long long)viol);
+#endif
+    for (; sidx < samples; sidx += samples_per_pass, off += row_step) {
+        T v[P];
+        const uint64_t id = id0 + (uint32_t)(sidx - lane_sample);
+        const unsigned pending = first_attempt<T>(kDrType, blk, seed, id, call, kTasks, j, v);
+        if (kDrType != kDrUniform && pending) viol += redraws<T>(kDrType, blk, seed, id, call, kTasks, j, pending, v);
+        store_block<T, kStore>(tile + off, v, blk.valid);
+    }
+    if (kDrType == kDrGaussian && viol && violations) atomicAdd(violations, (unsigned long long)viol);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -64,6 +64,18 @@ template <> struct Pack<float> {
     {
         u[0] = u01(r.x); u[1] = u01(r.y); u[2] = u01(r.z); u[3] = u01(r.w);
     }
+    // off + (hi - lo) * u with u = (r >> 8) * 2^-24.  `scale` arrives PRE-MULTIPLIED by 2^-24 (uniform_scale):
+    // a power-of-two factor is exact, so fma(scale, (float)(r >> 8), off) has the same real argument -- hence the
+    // same rounded result -- as fma(hi - lo, u, off), in one instruction less per value.
+    static constexpr float kUniformScale = 1.0f / 16777216.0f;
+    __device__ static __forceinline__ float uniform_scale(float width) { return width * kUniformScale; }
+    __device__ static __forceinline__ void uniform_affine(uint4 r, const float scale[4], const float off[4], float out[4])
+    {
+        out[0] = fmaf(scale[0], (float)(r.x >> 8), off[0]);
+        out[1] = fmaf(scale[1], (float)(r.y >> 8), off[1]);
+        out[2] = fmaf(scale[2], (float)(r.z >> 8), off[2]);
+        out[3] = fmaf(scale[3], (float)(r.w >> 8), off[3]);
+    }
     // 4 standard normals: Box-Muller on the pairs (x,y) and (z,w), both branches used
     __device__ static __forceinline__ void normals(uint4 r, float z[4])
     {
@@ -81,6 +93,15 @@ template <> struct Pack<double> {
     __device__ static __forceinline__ void uniforms(uint4 r, double u[2])
     {
         u[0] = u01(r.x, r.y); u[1] = u01(r.z, r.w);
+    }
+    // numpy: low + (high - low) * u, separately rounded
+    __device__ static __forceinline__ double uniform_scale(double width) { return width; }
+    __device__ static __forceinline__ void uniform_affine(uint4 r, const double scale[2], const double off[2], double out[2])
+    {
+        double u[2];
+        uniforms(r, u);
+        out[0] = __dadd_rn(off[0], __dmul_rn(scale[0], u[0]));
+        out[1] = __dadd_rn(off[1], __dmul_rn(scale[1], u[1]));
     }
     __device__ static __forceinline__ void normals(uint4 r, double z[2])
     {
