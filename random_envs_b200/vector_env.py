@@ -294,6 +294,7 @@ class RandomCartPoleVecEnv(RandomEnv):
             h["np"] = dict(action=h["action"].numpy()[:n], obs=h["state"].numpy()[:, :n].T,
                            reward=h["reward"].numpy()[:n], done=h["done"].numpy()[:n].view(np.bool_),
                            truncated=h["truncated"].numpy()[:n].view(np.bool_))
+            h["reward"].fill_(1)      # with auto-reset the reward is 1.0 on every step (:207-212): never copied
             h["stream"] = t.cuda.Stream(device=b["device"])
             h["event"] = t.cuda.Event()
             b["host"] = h
@@ -319,11 +320,19 @@ class RandomCartPoleVecEnv(RandomEnv):
             b["action"].copy_(h["action"], non_blocking=True)
             self.step(b["action"])
             h["state"].copy_(b["state"], non_blocking=True)
-            h["reward"].copy_(b["reward"], non_blocking=True)
+            if not self.auto_reset:        # only the steps-beyond-done rule (:213-222) ever yields 0.0
+                h["reward"].copy_(b["reward"], non_blocking=True)
             h["done"].copy_(b["done"], non_blocking=True)
             if self.track_truncated:
                 h["truncated"].copy_(b["truncated"], non_blocking=True)
             h["event"].record(stream)
+
+    def host_bytes_per_step(self):
+        """(host->device, device->host) bytes one ``step_host`` moves over PCIe."""
+        esize = 4 if self._dtype_name == "float32" else 8
+        ld = self._alloc()["ld"]
+        d2h = 4 * ld * esize + ld + (0 if self.auto_reset else ld * esize) + (ld if self.track_truncated else 0)
+        return ld, d2h
 
     def step_host_wait(self):
         """Block until the last ``step_host_async`` finished -> (obs (N,4), reward, done, truncated) numpy views."""

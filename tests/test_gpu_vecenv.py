@@ -251,6 +251,23 @@ def test_step_host_matches_step():
         assert np.array_equal(ht, _np(info["TimeLimit.truncated"]))
 
 
+def test_step_host_without_auto_reset_carries_the_zero_rewards():
+    """Only with auto-reset is the reward a host-side constant; the steps-beyond-done rule must cross PCIe."""
+    n = 515
+    dev = random_envs.RandomCartPoleVecEnv(n, dtype="float64", seed=9, auto_reset=False, max_episode_steps=0)
+    host = random_envs.RandomCartPoleVecEnv(n, dtype="float64", seed=9, auto_reset=False, max_episode_steps=0)
+    dev.reset(); host.reset()
+    zeros = 0
+    for k in range(60):
+        a = torch.ones(n, dtype=torch.uint8, device="cuda")            # constant push: everyone falls, then keeps stepping
+        o, r, d, _ = dev.step(a)
+        ho, hr, hd, _ = host.step_host(_np(a))
+        assert np.array_equal(hr, _np(r)) and np.array_equal(hd, _np(d)) and np.array_equal(ho, _np(o))
+        zeros += int((hr == 0).sum())
+    assert zeros > 0
+    assert host.host_bytes_per_step()[1] > dev.num_envs * (4 * 8 + 1 + 8)
+
+
 # ------------------------------------------------------------------------------------------------ drop-in
 def test_dropin_random_policy_loop_like_the_reference_demo():
     """test_random_policy.py:12-32 without rendering, plus README.md:52-66."""
