@@ -363,6 +363,21 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
         del env, a
         torch.cuda.empty_cache()
 
+    # Noisy variant: +16 B/env-step for the separate obs rows, one Philox block + Box-Muller per env
+    n = 1 << 24
+    env = renv.RandomCartPoleVecEnv(n, dtype="float32", device=dev, seed=1, env_id0=rank * n, track_truncated=False,
+                                    track_episodes=False, noisy=True, noise_level=1e-4)
+    env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True); env.reset()
+    a = env.sample_actions().clone()
+    for _ in range(3):
+        env.step(a)
+    ms = timed(lambda: [env.step(a) for _ in range(40)])
+    gbs = (BYTES_PER_STEP["float32"] + 16) * n * 40 / (ms * 1e-3) / 1e9
+    out["step_f32_noisy_16M"] = {"env_steps_per_s": agg(n * 40, ms), "launch_us": 1e3 * ms / 40, "gbs_per_gpu": gbs,
+                                 "frac_of_hbm_peak": gbs / peak, "envs_per_gpu": n, "bytes_per_env_step": 78}
+    del env, a
+    torch.cuda.empty_cache()
+
     # FP32 / FP64 FMA peaks for the rollout roofline
     sm = torch.cuda.get_device_properties(dev).multi_processor_count
     peaks = {}

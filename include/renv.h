@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RENV_ABI_VERSION 2
+#define RENV_ABI_VERSION 3
 #define RENV_MAX_DIM 32          /* largest task_dim in the suite is 30 (jinja/random_humanoid.py) */
 #define RENV_NUM_STATS 6         /* episodes, sum R, sum R^2, min R, max R, sum length */
 
@@ -121,6 +121,30 @@ int renv_cartpole_step_f32(const renv_cartpole_env *env, const uint8_t *action, 
 int renv_cartpole_step_f64(const renv_cartpole_env *env, const uint8_t *action, double *reward, uint8_t *done,
                            uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
                            const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
+
+/* Observation noise of the suite's "Noisy" env variants (jinja/random_hopper.py:28,107-108, random_half_cheetah.py,
+ * random_walker2d.py:139-140, random_humanoid.py:193-204): every observation -- after a step and after a reset --
+ * is  obs = state + sqrt(noise_level) * N(0, I);  the state itself is not perturbed.  The *_noisy entry points are
+ * the plain ones plus this block: `obs` is a DEVICE buffer T (4, ld), 16-byte aligned, that receives the noisy
+ * observation (with auto_reset a finished env's row holds the noisy observation of its reset state); `std` =
+ * sqrt(noise_level) >= 0.  Normals are Philox draws keyed (seed, env id, tick, purpose 4). */
+typedef struct renv_obs_noise {
+    void *obs;                   /* T (4, ld) */
+    double std;                  /* sqrt(noise_level) */
+} renv_obs_noise;
+
+int renv_cartpole_reset_noisy_f32(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *mask,
+                                  uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
+int renv_cartpole_reset_noisy_f64(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *mask,
+                                  uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
+int renv_cartpole_step_noisy_f32(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action,
+                                 float *reward, uint8_t *done, uint8_t *truncated, int integrator, int max_steps,
+                                 int auto_reset, uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations,
+                                 void *stream);
+int renv_cartpole_step_noisy_f64(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action,
+                                 double *reward, uint8_t *done, uint8_t *truncated, int integrator, int max_steps,
+                                 int auto_reset, uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations,
+                                 void *stream);
 
 /* K fused steps with the linear policy a = [w.s + b > 0] evaluated in-kernel, auto-reset always on.
  * State, xi and counters stay in registers for the K steps.  stats (device, RENV_NUM_STATS doubles,

@@ -16,7 +16,7 @@ SRC = os.path.join(_HERE, "cartpole_oracle.c")
 OUT_DIR = os.path.join(_HERE, "_build")
 LIB = os.path.join(OUT_DIR, "liboracle.so")
 
-PURPOSE_INIT, PURPOSE_XI, PURPOSE_ACTION, PURPOSE_TASKS = 0, 1, 2, 3
+PURPOSE_INIT, PURPOSE_XI, PURPOSE_ACTION, PURPOSE_TASKS, PURPOSE_OBS = 0, 1, 2, 3, 4
 
 
 def build(force=False):

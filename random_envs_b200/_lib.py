@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RENV_B200_LIB", os.path.join(_HERE, "librenv_b200.so"))   # override: kernel experiments
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_DIM = 32
 NUM_STATS = 6
 
@@ -35,9 +35,14 @@ class CartpoleEnv(ctypes.Structure):
                 ("env_id0", ctypes.c_uint64), ("seed", ctypes.c_uint64)]
 
 
+class ObsNoise(ctypes.Structure):
+    """struct renv_obs_noise (include/renv.h)."""
+    _fields_ = [("obs", ctypes.c_void_p), ("std", ctypes.c_double)]
+
+
 _vp, _i64, _u64, _u32, _int, _dbl = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint32,
                                      ctypes.c_int, ctypes.c_double)
-_cfg_p, _env_p = ctypes.POINTER(DrCfg), ctypes.POINTER(CartpoleEnv)
+_cfg_p, _env_p, _noise_p = ctypes.POINTER(DrCfg), ctypes.POINTER(CartpoleEnv), ctypes.POINTER(ObsNoise)
 
 # name -> (restype, argtypes); must list every function declared in include/renv.h
 SIGNATURES = {
@@ -49,6 +54,10 @@ SIGNATURES = {
     "renv_cartpole_reset_f64": (_int, [_env_p, _vp, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_step_f32": (_int, [_env_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_step_f64": (_int, [_env_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_reset_noisy_f32": (_int, [_env_p, _noise_p, _vp, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_reset_noisy_f64": (_int, [_env_p, _noise_p, _vp, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_step_noisy_f32": (_int, [_env_p, _noise_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_step_noisy_f64": (_int, [_env_p, _noise_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_rollout_f32": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_cartpole_rollout_f64": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_random_actions_u8": (_int, [_vp, _i64, _u64, _u64, _u32, _vp]),

@@ -48,6 +48,20 @@ template <typename T> int check_env(const renv_cartpole_env *env, bool need_beyo
     out->ld = env->ld;
     out->env_id0 = env->env_id0;
     out->seed = env->seed;
+    out->obs = nullptr;
+    out->noise_std = T(0);
+    return RENV_OK;
+}
+
+// "Noisy" variants: attach the observation buffer.  noise == nullptr: plain env (obs is the state itself).
+template <typename T> int attach_noise(const renv_obs_noise *noise, EnvPtrs<T> *env)
+{
+    if (noise == nullptr) return RENV_OK;
+    if (noise->obs == nullptr) return RENV_E_NULL;
+    if (!aligned(noise->obs, 16)) return RENV_E_ALIGN;
+    if (!(noise->std >= 0.0)) return RENV_E_ARG;
+    env->obs = static_cast<T *>(noise->obs);
+    env->noise_std = (T)noise->std;
     return RENV_OK;
 }
 
@@ -100,11 +114,13 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
 }
 
 template <typename T>
-int cartpole_reset(const renv_cartpole_env *env, const uint8_t *mask, uint64_t tick, const renv_dr_cfg *dr,
-                   unsigned long long *violations, void *stream)
+int cartpole_reset(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *mask, uint64_t tick,
+                   const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
 {
     ResetArgs<T> a;
     int rc = check_env<T>(env, false, &a.env);
+    if (rc) return rc;
+    rc = attach_noise<T>(noise, &a.env);
     if (rc) return rc;
     rc = to_cfg4(dr, &a.dr);
     if (rc) return rc;
@@ -118,12 +134,14 @@ int cartpole_reset(const renv_cartpole_env *env, const uint8_t *mask, uint64_t t
 }
 
 template <typename T>
-int cartpole_step(const renv_cartpole_env *env, const uint8_t *action, T *reward, uint8_t *done, uint8_t *truncated,
-                  int integrator, int max_steps, int auto_reset, uint64_t tick, const renv_dr_cfg *dr,
-                  unsigned long long *violations, void *stream)
+int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action, T *reward,
+                  uint8_t *done, uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
+                  const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
 {
     StepArgs<T> a;
     int rc = check_env<T>(env, !auto_reset, &a.env);
+    if (rc) return rc;
+    rc = attach_noise<T>(noise, &a.env);
     if (rc) return rc;
     if (action == nullptr || reward == nullptr || done == nullptr) return RENV_E_NULL;
     if (!aligned(action, 4) || !aligned(reward, 16) || !aligned(done, 4) || (truncated && !aligned(truncated, 4)))
@@ -139,10 +157,12 @@ int cartpole_step(const renv_cartpole_env *env, const uint8_t *action, T *reward
     constexpr int64_t per_block = (int64_t)kStepThreads * VecTraits<T>::V;
     const int64_t blocks = (env->n + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
-    if (auto_reset)
-        cartpole_step_kernel<T, true><<<(unsigned)blocks, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-    else
-        cartpole_step_kernel<T, false><<<(unsigned)blocks, kStepThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool noisy = a.env.obs != nullptr;
+    if (auto_reset && !noisy) cartpole_step_kernel<T, true, false><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
+    else if (auto_reset) cartpole_step_kernel<T, true, true><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
+    else if (!noisy) cartpole_step_kernel<T, false, false><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
+    else cartpole_step_kernel<T, false, true><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
     return launch_status();
 }
 
@@ -238,27 +258,58 @@ int renv_dr_sample_f64(double *out, int64_t n, const renv_dr_cfg *cfg, uint64_t 
 int renv_cartpole_reset_f32(const renv_cartpole_env *env, const uint8_t *mask, uint64_t tick, const renv_dr_cfg *dr,
                             unsigned long long *violations, void *stream)
 {
-    return cartpole_reset<float>(env, mask, tick, dr, violations, stream);
+    return cartpole_reset<float>(env, nullptr, mask, tick, dr, violations, stream);
 }
 int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, uint64_t tick, const renv_dr_cfg *dr,
                             unsigned long long *violations, void *stream)
 {
-    return cartpole_reset<double>(env, mask, tick, dr, violations, stream);
+    return cartpole_reset<double>(env, nullptr, mask, tick, dr, violations, stream);
 }
 
 int renv_cartpole_step_f32(const renv_cartpole_env *env, const uint8_t *action, float *reward, uint8_t *done,
                            uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
                            const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
 {
-    return cartpole_step<float>(env, action, reward, done, truncated, integrator, max_steps, auto_reset, tick, dr,
-                                violations, stream);
+    return cartpole_step<float>(env, nullptr, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
+                                dr, violations, stream);
 }
 int renv_cartpole_step_f64(const renv_cartpole_env *env, const uint8_t *action, double *reward, uint8_t *done,
                            uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
                            const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
 {
-    return cartpole_step<double>(env, action, reward, done, truncated, integrator, max_steps, auto_reset, tick, dr,
-                                 violations, stream);
+    return cartpole_step<double>(env, nullptr, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
+                                 dr, violations, stream);
+}
+
+int renv_cartpole_reset_noisy_f32(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *mask,
+                                  uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
+{
+    if (noise == nullptr) return RENV_E_NULL;
+    return cartpole_reset<float>(env, noise, mask, tick, dr, violations, stream);
+}
+int renv_cartpole_reset_noisy_f64(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *mask,
+                                  uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
+{
+    if (noise == nullptr) return RENV_E_NULL;
+    return cartpole_reset<double>(env, noise, mask, tick, dr, violations, stream);
+}
+int renv_cartpole_step_noisy_f32(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action,
+                                 float *reward, uint8_t *done, uint8_t *truncated, int integrator, int max_steps,
+                                 int auto_reset, uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations,
+                                 void *stream)
+{
+    if (noise == nullptr) return RENV_E_NULL;
+    return cartpole_step<float>(env, noise, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
+                                dr, violations, stream);
+}
+int renv_cartpole_step_noisy_f64(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action,
+                                 double *reward, uint8_t *done, uint8_t *truncated, int integrator, int max_steps,
+                                 int auto_reset, uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations,
+                                 void *stream)
+{
+    if (noise == nullptr) return RENV_E_NULL;
+    return cartpole_step<double>(env, noise, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
+                                 dr, violations, stream);
 }
 
 int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,

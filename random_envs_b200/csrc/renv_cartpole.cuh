@@ -235,6 +235,28 @@ __device__ __forceinline__ void init_state(State<double> &s, uint64_t seed, uint
     s.theta_dot = __dadd_rn(-0.05, __dmul_rn(0.1, v[1]));
 }
 
+// ---- observation noise of the suite's "Noisy" variants: obs = state + sqrt(noise_level) * N(0, I) ----------
+// (jinja/random_hopper.py:107-108, random_walker2d.py:139-140, random_humanoid.py:193-204; drawn on every
+// _get_obs, i.e. after a step AND after a reset.)  Four normals keyed (seed, id, tick, kObs); `which` = 0 for the
+// observation of a step, 1 for the observation of the reset that may follow it at the same tick.
+__device__ __forceinline__ void add_obs_noise(const State<float> &s, float std, uint64_t seed, uint64_t id, uint64_t tick,
+                                              uint32_t which, float o[4])
+{
+    float z[4];
+    Num<float>::normals(draw_block(seed, id, tick, kObs, which * 16u), z);
+    o[0] = fmaf(std, z[0], s.x); o[1] = fmaf(std, z[1], s.x_dot);
+    o[2] = fmaf(std, z[2], s.theta); o[3] = fmaf(std, z[3], s.theta_dot);
+}
+__device__ __forceinline__ void add_obs_noise(const State<double> &s, double std, uint64_t seed, uint64_t id, uint64_t tick,
+                                              uint32_t which, double o[4])
+{
+    double z[4];
+    Pack<double>::normals(draw_block(seed, id, tick, kObs, which * 16u), z);
+    Pack<double>::normals(draw_block(seed, id, tick, kObs, which * 16u + 1u), z + 2);
+    o[0] = __dadd_rn(s.x, __dmul_rn(std, z[0])); o[1] = __dadd_rn(s.x_dot, __dmul_rn(std, z[1]));      // obs += std * randn
+    o[2] = __dadd_rn(s.theta, __dmul_rn(std, z[2])); o[3] = __dadd_rn(s.theta_dot, __dmul_rn(std, z[3]));
+}
+
 // fullgaussian for the 4-dim cart-pole xi: x = mean + F z in the normalised space, clip, denormalise.
 // Deliberately NOT inlined: it is the rarest branch of the (already cold) reset path and inlining it costs the
 // fused rollout kernel 40 registers.  `cfg` points into the kernel's __grid_constant__ parameter block.

@@ -66,6 +66,7 @@ __device__ __forceinline__ void store_xi(double *xi, int64_t i, const Xi<double>
 template <typename T> struct EnvPtrs {
     T *state; T *xi; int32_t *elapsed; uint32_t *episode; int32_t *beyond;
     int64_t n, ld; uint64_t env_id0, seed;
+    T *obs; T noise_std;      // "Noisy" variants: obs (4, ld) = state + noise_std * N(0, I); obs == nullptr: obs IS state
 };
 
 // RandomCartPoleEnv.reset (+ set_random_task) of env i at clock `tick`; scalar stores.
@@ -78,6 +79,11 @@ __device__ __forceinline__ unsigned reset_env(const EnvPtrs<T> &env, const DrCfg
     init_state(st, env.seed, id, tick);
     env.state[0 * ld + i] = st.x; env.state[1 * ld + i] = st.x_dot;
     env.state[2 * ld + i] = st.theta; env.state[3 * ld + i] = st.theta_dot;
+    if (env.obs) {                                         // noisy observation of the reset state (_get_obs in reset_model)
+        T o[4];
+        add_obs_noise(st, env.noise_std, env.seed, id, tick, 1u, o);
+        env.obs[0 * ld + i] = o[0]; env.obs[1 * ld + i] = o[1]; env.obs[2 * ld + i] = o[2]; env.obs[3 * ld + i] = o[3];
+    }
     unsigned viol = 0;
     if (dr.dr_type != kDrNone) {
         Xi<T> xi = { T(0), T(0), T(0), T(0) };
@@ -106,7 +112,7 @@ constexpr int kStepThreads = 256;
 // run the ~250-instruction Philox/sampling path once per warp per finished lane with ~1 active lane): their
 // CTA-local indices are appended to a shared-memory list and, after one __syncthreads, the first `count`
 // threads of the CTA each reset one env at full lane utilisation, overwriting the owner's stores.
-template <typename T, bool kAutoReset>
+template <typename T, bool kAutoReset, bool kNoisy = false>
 __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpole_step_kernel(const __grid_constant__ StepArgs<T> a)
 {
     using VT = VecTraits<T>;
@@ -170,6 +176,29 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpo
             if (kAutoReset && done && i0 + v < n) {
                 el[v] = 0;
                 s_list[atomicAdd(&s_count, 1u)] = (uint16_t)(threadIdx.x * V + v);
+            }
+        }
+
+        if (kNoisy) {       // obs = new state + std * N(0, I); a finished env's obs is overwritten by its reset below
+            T o[4][V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                T ov[4];
+                add_obs_noise(State<T>{ s[0][v], s[1][v], s[2][v], s[3][v] }, a.env.noise_std, a.env.seed,
+                              a.env.env_id0 + (uint64_t)(i0 + v), a.tick, 0u, ov);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[c][v] = ov[c];
+            }
+            if (full) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) vstore<typename VT::Real>(a.env.obs + c * ld + i0, o[c]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (i0 + v < n) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) a.env.obs[c * ld + i0 + v] = o[c][v];
+                    }
             }
         }
 

@@ -27,8 +27,12 @@ from .vector_env import (MAX_EPISODE_STEPS, NOMINAL_TASK, THETA_THRESHOLD_RADIAN
 class RandomCartPoleEnv(RandomEnv):
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 50}
 
-    def __init__(self, device=None, resample_on_reset=True):
+    def __init__(self, noisy=False, device=None, resample_on_reset=True):
         RandomEnv.__init__(self)
+        # `noisy` / `noise_level` as in the suite's MuJoCo envs (e.g. jinja/random_hopper.py:16,21-28,107-108); the
+        # reference has no noisy cart-pole, RandomCartPoleNoisy-v0 is this framework's sibling of RandomHopperNoisy-v0
+        self.noisy = noisy
+        self.noise_level = 1e-4
         self.gravity, self.cart_mass, self.pole_mass, self.pole_length = NOMINAL_TASK
         self.total_mass = self.pole_mass + self.cart_mass
         self.polemass_length = self.pole_mass * self.pole_length   # never refreshed by set_task (:79, :157-166)
@@ -54,7 +58,7 @@ class RandomCartPoleEnv(RandomEnv):
         self.reward_threshold = 500
         self.resample_on_reset = resample_on_reset
         self._core = RandomCartPoleVecEnv(1, dtype="float64", device=device, max_episode_steps=0, auto_reset=False,
-                                          track_truncated=False)
+                                          track_truncated=False, noisy=bool(noisy), noise_level=self.noise_level)
         self._pushed = None     # (state, task) last written to the device, to skip redundant uploads
         self.seed()
 
@@ -83,6 +87,7 @@ class RandomCartPoleEnv(RandomEnv):
         """Upload host-visible attributes the user may have assigned (env.state = ..., set_task)."""
         core = self._core
         core.kinematics_integrator = self.kinematics_integrator
+        core.noise_level = float(self.noise_level)
         task = (float(self.gravity), float(self.cart_mass), float(self.pole_mass), float(self.pole_length))
         state = tuple(float(v) for v in self.state)
         beyond = -1 if self.steps_beyond_done is None else int(self.steps_beyond_done)
@@ -100,10 +105,11 @@ class RandomCartPoleEnv(RandomEnv):
         was_beyond = self.steps_beyond_done
         t = _device.torch()
         obs, reward, done, _ = self._core.step(t.tensor([int(action)], dtype=t.uint8))
-        packed = t.cat([obs.reshape(-1), reward.reshape(-1), done.reshape(-1).to(t.float64),
-                        self._core.steps_beyond_done.to(t.float64)]).cpu().numpy()
+        packed = t.cat([self._core.state.reshape(-1), reward.reshape(-1), done.reshape(-1).to(t.float64),
+                        self._core.steps_beyond_done.to(t.float64), obs.reshape(-1)]).cpu().numpy()
         self.state = tuple(float(v) for v in packed[:4])
         reward, done, beyond = float(packed[4]), bool(packed[5]), int(packed[6])
+        observation = packed[7:11].copy() if self.noisy else np.array(self.state)
         self.steps_beyond_done = None if beyond < 0 else beyond
         if was_beyond == 0 and done:
             logger.warn("You are calling 'step()' even though this environment has already returned done = True. "
@@ -111,7 +117,7 @@ class RandomCartPoleEnv(RandomEnv):
                         "undefined behavior.")
         self._pushed = (self.state, (float(self.gravity), float(self.cart_mass), float(self.pole_mass),
                                      float(self.pole_length)), beyond)
-        return np.array(self.state), reward, done, {}
+        return observation, reward, done, {}
 
     def reset(self):
         if self.dr_training and self.resample_on_reset and self.sampling is not None:
@@ -119,13 +125,15 @@ class RandomCartPoleEnv(RandomEnv):
         # s0 ~ U(-0.05, 0.05)^4 drawn by the reset kernel (Philox keyed by seed / episode)
         core = self._core
         core.kinematics_integrator = self.kinematics_integrator
+        core.noise_level = float(self.noise_level)
         obs = core.reset()
-        self.state = tuple(float(v) for v in obs.reshape(-1).cpu().numpy())
+        self.state = tuple(float(v) for v in core.state.reshape(-1).cpu().numpy())
+        observation = obs.reshape(-1).cpu().numpy().copy() if self.noisy else np.array(self.state)
         self.steps_beyond_done = None
         core.set_task(float(self.gravity), float(self.cart_mass), float(self.pole_mass), float(self.pole_length))
         self._pushed = (self.state, (float(self.gravity), float(self.cart_mass), float(self.pole_mass),
                                      float(self.pole_length)), -1)
-        return np.array(self.state)
+        return observation
 
     def render(self, mode="human"):
         raise NotImplementedError("rendering (pyglet viewer, random_cartpole.py:231-288) is out of scope")
@@ -139,4 +147,11 @@ gym_compat.register(
     entry_point="%s:RandomCartPoleEnv" % __name__,
     max_episode_steps=MAX_EPISODE_STEPS,
     kwargs={},
+)
+# the suite's naming for the observation-noise siblings (jinja/random_hopper.py:161-166 RandomHopperNoisy-v0)
+gym_compat.register(
+    id="RandomCartPoleNoisy-v0",
+    entry_point="%s:RandomCartPoleEnv" % __name__,
+    max_episode_steps=MAX_EPISODE_STEPS,
+    kwargs={"noisy": True},
 )

@@ -45,7 +45,7 @@ class RandomCartPoleVecEnv(RandomEnv):
 
     def __init__(self, num_envs, dtype="float32", device=None, seed=0, env_id0=0,
                  max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, kinematics_integrator="euler",
-                 track_truncated=True, validate_actions=False, track_episodes=True):
+                 track_truncated=True, validate_actions=False, track_episodes=True, noisy=False, noise_level=1e-4):
         RandomEnv.__init__(self)
         if num_envs <= 0:
             raise ValueError("num_envs must be positive")
@@ -62,6 +62,11 @@ class RandomCartPoleVecEnv(RandomEnv):
         self.track_truncated = bool(track_truncated)
         self.validate_actions = bool(validate_actions)
         self.track_episodes = bool(track_episodes)
+        # the suite's "Noisy" variants (jinja/random_hopper.py:16,28,107-108): obs = state + sqrt(noise_level) * N(0, I)
+        self.noisy = bool(noisy)
+        self.noise_level = float(noise_level)
+        if self.noise_level < 0:
+            raise ValueError("noise_level must be >= 0")
 
         self.dyn_ind_to_name = dict(enumerate(_TABLE.names))
         self.original_task = np.array(NOMINAL_TASK)
@@ -115,6 +120,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         b["truncated"] = t.zeros(ld, dtype=t.uint8, device=dev)
         b["action"] = t.zeros(ld, dtype=t.uint8, device=dev)
         b["stats"] = t.tensor([0.0, 0.0, 0.0, math.inf, -math.inf, 0.0], dtype=t.float64, device=dev)
+        b["obs"] = t.zeros((4, ld), dtype=dt, device=dev) if self.noisy else None
         b["env"] = None
         self._buffers = b
         self._refresh_env_struct()
@@ -129,6 +135,18 @@ class RandomCartPoleVecEnv(RandomEnv):
         env.n, env.ld = self.num_envs, b["ld"]
         env.env_id0, env.seed = self.env_id0, self._seed
         b["env"] = env
+        b["noise"] = None
+        if self.noisy:
+            b["noise"] = _lib.ObsNoise()
+            b["noise"].obs, b["noise"].std = b["obs"].data_ptr(), math.sqrt(self.noise_level)
+
+    def _entry(self, name):
+        """(function name, leading arguments): the *_noisy entry points take the obs-noise block after env."""
+        b = self._buffers
+        if self.noisy:
+            b["noise"].std = math.sqrt(self.noise_level)      # noise_level is a plain attribute in the reference
+            return "renv_cartpole_%s_noisy_%s" % (name, self._suffix()), (ctypes.byref(b["env"]), ctypes.byref(b["noise"]))
+        return "renv_cartpole_%s_%s" % (name, self._suffix()), (ctypes.byref(b["env"]),)
 
     def _suffix(self):
         return "f32" if self._dtype_name == "float32" else "f64"
@@ -168,16 +186,23 @@ class RandomCartPoleVecEnv(RandomEnv):
             assert mask.shape == (self.num_envs,)
             mask_ptr = _device.ptr(mask)
         viol = self._violation_counter(b["device"])
+        fn, head = self._entry("reset")
         with t.cuda.device(b["device"]):
-            _lib.call("renv_cartpole_reset_" + self._suffix(), ctypes.byref(b["env"]), mask_ptr, self._tick,
+            _lib.call(fn, *head, mask_ptr, self._tick,
                       self._active_dr_cfg(), _device.ptr(viol), _device.stream_ptr(b["device"]))
         self._tick += 1
         return self.obs
 
     @property
     def obs(self):
+        """(N, 4) view of the last observation: the state itself, or the noisy copy for the Noisy variant."""
         b = self._alloc()
-        return b["state"][:, :self.num_envs].t()
+        return (b["obs"] if self.noisy else b["state"])[:, :self.num_envs].t()
+
+    @property
+    def state(self):
+        """(N, 4) view of the true state (what the dynamics integrate; equals ``obs`` unless ``noisy``)."""
+        return self._alloc()["state"][:, :self.num_envs].t()
 
     def _stage_actions(self, actions):
         b = self._buffers
@@ -205,8 +230,9 @@ class RandomCartPoleVecEnv(RandomEnv):
         staged = self._stage_actions(actions)
         viol = self._violation_counter(b["device"])
         n = self.num_envs
+        fn, head = self._entry("step")
         with t.cuda.device(b["device"]):
-            _lib.call("renv_cartpole_step_" + self._suffix(), ctypes.byref(b["env"]), _device.ptr(staged),
+            _lib.call(fn, *head, _device.ptr(staged),
                       _device.ptr(b["reward"]), _device.ptr(b["done"]),
                       _device.ptr(b["truncated"]) if self.track_truncated else None,
                       self._integrator(), self.max_episode_steps, int(self.auto_reset), self._tick,
@@ -231,6 +257,9 @@ class RandomCartPoleVecEnv(RandomEnv):
         """K fused env-steps under the in-kernel linear policy a = [w.s + b > 0] (auto-reset always on)."""
         buf = self._alloc()
         t = _device.torch()
+        if self.noisy:
+            raise NotImplementedError("the fused rollout evaluates its policy on the true state; step() the Noisy "
+                                      "variant instead")
         w_arr = (ctypes.c_double * 4)(*[float(v) for v in w])
         viol = self._violation_counter(buf["device"])
         with t.cuda.device(buf["device"]):
@@ -319,7 +348,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         with t.cuda.stream(stream):
             b["action"].copy_(h["action"], non_blocking=True)
             self.step(b["action"])
-            h["state"].copy_(b["state"], non_blocking=True)
+            h["state"].copy_(b["obs"] if self.noisy else b["state"], non_blocking=True)
             if not self.auto_reset:        # only the steps-beyond-done rule (:213-222) ever yields 0.0
                 h["reward"].copy_(b["reward"], non_blocking=True)
             h["done"].copy_(b["done"], non_blocking=True)
