@@ -135,6 +135,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         env.n, env.ld = self.num_envs, b["ld"]
         env.env_id0, env.seed = self.env_id0, self._seed
         b["env"] = env
+        b["step_plan"] = None          # holds byref(env): rebuild
         b["noise"] = None
         if self.noisy:
             b["noise"] = _lib.ObsNoise()
@@ -223,25 +224,52 @@ class RandomCartPoleVecEnv(RandomEnv):
             raise AssertionError("%r (%s) invalid" % (actions, type(actions)))
         return staged
 
+    def _step_plan(self):
+        """Everything about a ``step`` launch that does not change between calls: the bound C function, the ctypes
+        pointers of the persistent buffers and the views handed back.  Rebuilt when a layout-affecting attribute
+        changes.  (A 2^20-env step is an 11 us kernel: per-call Python work has to stay below that.)"""
+        b = self._buffers
+        key = (self.noisy, self.track_truncated, self._dtype_name)
+        plan = b.get("step_plan")
+        if plan is not None and plan["key"] == key:
+            return plan
+        t = _device.torch()
+        n = self.num_envs
+        fn, head = self._entry("step")
+        info = {"TimeLimit.truncated": b["truncated"][:n].view(t.bool)} if self.track_truncated else {}
+        plan = dict(key=key, fn=getattr(_lib.load(), fn), name=fn, head=head,
+                    reward=_device.ptr(b["reward"]), done=_device.ptr(b["done"]),
+                    truncated=_device.ptr(b["truncated"]) if self.track_truncated else None,
+                    out=(self.obs, b["reward"][:n], b["done"][:n].view(t.bool)), info=info,
+                    device_index=b["device"].index)
+        b["step_plan"] = plan
+        return plan
+
     def step(self, actions):
-        """One env-step for all N envs.  actions: (N,) integer tensor/array in {0, 1}."""
+        """One env-step for all N envs.  actions: (N,) integer tensor/array in {0, 1}.
+
+        Returns (obs (N, 4), reward (N,), done (N,) bool, info) -- views of the env's own buffers, refreshed in place
+        by every step (as the reference's obs aliases its state, random_cartpole.py:224)."""
         b = self._alloc()
         t = _device.torch()
         staged = self._stage_actions(actions)
         viol = self._violation_counter(b["device"])
-        n = self.num_envs
-        fn, head = self._entry("step")
-        with t.cuda.device(b["device"]):
-            _lib.call(fn, *head, _device.ptr(staged),
-                      _device.ptr(b["reward"]), _device.ptr(b["done"]),
-                      _device.ptr(b["truncated"]) if self.track_truncated else None,
-                      self._integrator(), self.max_episode_steps, int(self.auto_reset), self._tick,
-                      self._active_dr_cfg(), _device.ptr(viol), _device.stream_ptr(b["device"]))
+        plan = self._step_plan()
+        if self.noisy:
+            b["noise"].std = math.sqrt(self.noise_level)
+        args = plan["head"] + (ctypes.c_void_p(staged.data_ptr()), plan["reward"], plan["done"], plan["truncated"],
+                               self._integrator(), self.max_episode_steps, int(self.auto_reset), self._tick,
+                               self._active_dr_cfg(), ctypes.c_void_p(viol.data_ptr()), _device.stream_ptr(b["device"]))
+        if t.cuda.current_device() == plan["device_index"]:
+            rc = plan["fn"](*args)
+        else:
+            with t.cuda.device(b["device"]):
+                rc = plan["fn"](*args)
+        if rc != _lib.OK:
+            raise _lib.RenvError(plan["name"], rc, _lib.strerror(rc))
         self._tick += 1
-        info = {}
-        if self.track_truncated:
-            info["TimeLimit.truncated"] = b["truncated"][:n].view(t.bool)
-        return self.obs, b["reward"][:n], b["done"][:n].view(t.bool), info
+        obs, reward, done = plan["out"]
+        return obs, reward, done, dict(plan["info"])
 
     def sample_actions(self, out=None):
         """``action_space.sample()`` for every env: (N,) uint8 Bernoulli(1/2), Philox keyed by the step clock."""
