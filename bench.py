@@ -397,6 +397,7 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
         env = renv.RandomCartPoleVecEnv(n, dtype=dtype, device=dev, seed=2, env_id0=rank * n)
         env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True); env.reset()
         env.rollout(w, 0.0, 10)
+        renv.allgather_stats(env.stats_tensor)      # untimed: the first collective sets up NCCL's communicator / channels
         env.reset_stats()
 
         def it():
