@@ -3,7 +3,11 @@
 #include "../../include/renv.h"
 #include "renv_kernels.cuh"
 #include "renv_rollout_pair.cuh"
+#include "renv_step_bulk.cuh"
 
+#ifndef RENV_STEP_F32_BULK
+#define RENV_STEP_F32_BULK 0        // 1: fp32 auto-reset step through cp.async.bulk tiles (renv_step_bulk.cuh)
+#endif
 #ifndef RENV_ROLLOUT_F32_PAIR
 #define RENV_ROLLOUT_F32_PAIR 1     // 0: one env per thread (scalar FFMA) for A/B timing
 #endif
@@ -133,6 +137,28 @@ int cartpole_reset(const renv_cartpole_env *env, const renv_obs_noise *noise, co
     return launch_status();
 }
 
+// fp32 auto-reset step through bulk-async tiles: full 1024-env tiles by the bulk kernel, the remainder by the LDG/STG one
+int launch_step_bulk(const StepArgs<double> &, cudaStream_t) { return RENV_E_ARG; }
+int launch_step_bulk(const StepArgs<float> &a, cudaStream_t st)
+{
+    const int64_t tiles = a.env.n / kBulkTile, rest = a.env.n - tiles * kBulkTile;
+    if (tiles > 0x7fffffffLL) return RENV_E_SIZE;
+    if (tiles > 0) cartpole_step_bulk_kernel<<<(unsigned)tiles, kBulkThreads, 0, st>>>(a);
+    if (rest > 0) {
+        StepArgs<float> r = a;
+        const int64_t i0 = tiles * kBulkTile;
+        r.env.state += i0; r.env.xi += 4 * i0; r.env.elapsed += i0;
+        if (r.env.episode) r.env.episode += i0;
+        if (r.env.beyond) r.env.beyond += i0;
+        r.env.n = rest; r.env.env_id0 += (uint64_t)i0;
+        r.action += i0; r.reward += i0; r.done += i0;
+        if (r.truncated) r.truncated += i0;
+        const int64_t blocks = (rest + kStepThreads * 4 - 1) / (kStepThreads * 4);
+        cartpole_step_kernel<float, true, false><<<(unsigned)blocks, kStepThreads, 0, st>>>(r);
+    }
+    return launch_status();
+}
+
 template <typename T>
 int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action, T *reward,
                   uint8_t *done, uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
@@ -159,6 +185,7 @@ int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, con
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool noisy = a.env.obs != nullptr;
+    if (RENV_STEP_F32_BULK && sizeof(T) == 4 && auto_reset && !noisy) return launch_step_bulk(a, st);
     if (auto_reset && !noisy) cartpole_step_kernel<T, true, false><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
     else if (auto_reset) cartpole_step_kernel<T, true, true><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
     else if (!noisy) cartpole_step_kernel<T, false, false><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
