@@ -470,9 +470,6 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 // doubles = one Philox call); values go to a shared-memory tile that is contiguous in the output, so
 // the tile is written back with fully coalesced 128-bit stores whatever `dim` is (30 is not a
 // multiple of 4: a thread-per-sample store would touch 32 sectors per instruction).
-#ifndef RENV_SAMPLER_ILP2
-#define RENV_SAMPLER_ILP2 0
-#endif
 constexpr int kSampleThreads = 256;
 // Samples per CTA: every thread produces kItemsPerThread work items whatever `dim` is (dim 30: 256 float / 128 double
 // samples; dim 4: 2048 / 1024), so the per-thread set-up (12 parameter conversions) is amortised for the 3..4-dim
@@ -549,21 +546,8 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
     T *const tile = out + (first + lane_sample) * dim + j * P;      // 64-bit once; 32-bit offsets inside the tile
     const int row_step = samples_per_pass * dim;
     const uint64_t id0 = sample_id0 + (uint64_t)(first + lane_sample);
-    // first block of the last (possibly shorter) row: its valid mask drops the dims beyond `dim`
+    // (two interleaved Philox chains per thread were tried: no gain, the limit is IMAD.WIDE issue, not latency)
     int sidx = lane_sample, off = 0;
-#if RENV_SAMPLER_ILP2
-    // two independent Philox chains per iteration (a block is a ~100-cycle dependent IMAD.WIDE -> LOP3 chain)
-    for (; sidx + samples_per_pass < samples; sidx += 2 * samples_per_pass, off += 2 * row_step) {
-        T v0[P], v1[P];
-        const uint64_t id = id0 + (uint32_t)(sidx - lane_sample), id1 = id + (uint32_t)samples_per_pass;
-        const unsigned pend0 = first_attempt<T>(kDrType, blk, seed, id, call, kTasks, j, v0);
-        const unsigned pend1 = first_attempt<T>(kDrType, blk, seed, id1, call, kTasks, j, v1);
-        if (kDrType != kDrUniform && pend0) viol += redraws<T>(kDrType, blk, seed, id, call, kTasks, j, pend0, v0);
-        if (kDrType != kDrUniform && pend1) viol += redraws<T>(kDrType, blk, seed, id1, call, kTasks, j, pend1, v1);
-        store_block<T, kStore>(tile + off, v0, blk.valid);
-        store_block<T, kStore>(tile + off + row_step, v1, blk.valid);
-    }
-#endif
     for (; sidx < samples; sidx += samples_per_pass, off += row_step) {
         T v[P];
         const uint64_t id = id0 + (uint32_t)(sidx - lane_sample);
