@@ -23,9 +23,10 @@ from .distributed import allgather_stats, combine_stats, make_sharded_env, shard
 from .random_cartpole import RandomCartPoleEnv
 from .random_env import RandomEnv, TaskSampler
 from .vector_env import RandomCartPoleVecEnv
+from .gym_vector import RandomCartPoleGymVectorEnv
 from .xi_tables import HUMANOID_NOMINAL, XI_TABLES
 
-__all__ = ["gym", "RandomEnv", "TaskSampler", "RandomCartPoleEnv", "RandomCartPoleVecEnv", "XI_TABLES",
+__all__ = ["gym", "RandomEnv", "TaskSampler", "RandomCartPoleEnv", "RandomCartPoleVecEnv", "RandomCartPoleGymVectorEnv", "XI_TABLES",
            "HUMANOID_NOMINAL", "shard_range", "combine_stats", "summarize_stats", "allgather_stats",
            "make_sharded_env", "load_library"]
 

@@ -264,6 +264,17 @@ if HAVE_REAL_GYM:  # pragma: no cover
     make = _real_gym.make
 
 
+class _LazyVector:
+    """``gym.vector``: resolved on first use (gym_vector imports this module)."""
+
+    def __getattr__(self, name):
+        from . import gym_vector
+        return getattr(gym_vector, name)
+
+
+vector = _LazyVector()
+
+
 def install_as_gym():
     """Make ``import gym`` resolve to this module (only when no real gym exists)."""
     if not HAVE_REAL_GYM:
