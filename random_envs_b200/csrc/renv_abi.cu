@@ -205,7 +205,7 @@ int launch_rollout(const RolloutArgs<double> &a, cudaStream_t stream)
 int launch_rollout(const RolloutArgs<float> &a, cudaStream_t stream)
 {
 #if RENV_ROLLOUT_F32_PAIR
-    const int64_t threads = (a.env.n + 1) / 2;
+    const int64_t threads = (a.env.n + kPairSlots - 1) / kPairSlots;
     const int64_t blocks = (threads + kRolloutThreads - 1) / kRolloutThreads;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
     if (a.euler) cartpole_rollout_pair_kernel<true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);

@@ -66,11 +66,65 @@ __device__ __forceinline__ void slot_params(PairSlot &q, const Xi<float> &p)
     q.l43 = d.len_four_thirds; q.nlpm = -d.len_pm_over_total;
 }
 
+// Loop-invariant packed operands of the step (policy weights from the kernel parameters, polynomial coefficients).
+struct PairConsts {
+    u64 W0, W1, W2, W3, WB, C120, CM6, CM720, C24, CMH, ONE, TAU, NTAU;
+};
+
+// One env-step for the env pair (s0, s1): policy_action<float> + sincos_small<true> + dynamics<float>, every operation
+// the packed twin of the scalar one in renv_cartpole.cuh.  NNUM = -num and NTHACC = -theta_acc (exact: rounding is
+// sign-symmetric), so no negation instructions are needed.
+template <bool kEuler>
+__device__ __forceinline__ void pair_step(PairSlot &s0, PairSlot &s1, const PairConsts &k)
+{
+    u64 X = pk(s0.x, s1.x), XD = pk(s0.xd, s1.xd), TH = pk(s0.th, s1.th), THD = pk(s0.thd, s1.thd);
+    const u64 NG = pk(s0.ng, s1.ng), PMLOT = pk(s0.pmlot, s1.pmlot), L43 = pk(s0.l43, s1.l43), NLPM = pk(s0.nlpm, s1.nlpm);
+    u64 acc = fma2(k.W0, X, k.WB);
+    acc = fma2(k.W1, XD, acc);
+    acc = fma2(k.W2, TH, acc);
+    acc = fma2(k.W3, THD, acc);
+    float acc0, acc1;
+    unpk(acc, acc0, acc1);
+    const u64 PUSH = pk(acc0 > 0.0f ? s0.fot : -s0.fot, acc1 > 0.0f ? s1.fot : -s1.fot);
+    const u64 X2 = mul2(TH, TH);
+    const u64 PS = fma2(X2, k.C120, k.CM6);
+    const u64 SN = fma2(mul2(TH, X2), PS, TH);
+    u64 PC = fma2(X2, k.CM720, k.C24);
+    PC = fma2(X2, PC, k.CMH);
+    const u64 CS = fma2(X2, PC, k.ONE);
+    const u64 TEMP = fma2(mul2(mul2(THD, THD), SN), PMLOT, PUSH);
+    const u64 NNUM = fma2(NG, SN, mul2(CS, TEMP));
+    const u64 DEN = fma2(NLPM, mul2(CS, CS), L43);
+    float den0, den1;
+    unpk(DEN, den0, den1);
+    const u64 NTHACC = mul2(NNUM, pk(rcp_approx(den0), rcp_approx(den1)));
+    const u64 XACC = fma2(mul2(PMLOT, CS), NTHACC, TEMP);
+    if (kEuler) {
+        X = fma2(k.TAU, XD, X);
+        XD = fma2(k.TAU, XACC, XD);
+        TH = fma2(k.TAU, THD, TH);
+        THD = fma2(k.NTAU, NTHACC, THD);
+    } else {
+        XD = fma2(k.TAU, XACC, XD);
+        X = fma2(k.TAU, XD, X);
+        THD = fma2(k.NTAU, NTHACC, THD);
+        TH = fma2(k.TAU, THD, TH);
+    }
+    unpk(X, s0.x, s1.x); unpk(XD, s0.xd, s1.xd); unpk(TH, s0.th, s1.th); unpk(THD, s0.thd, s1.thd);
+}
+
+#ifndef RENV_PAIR_GROUPS
+#define RENV_PAIR_GROUPS 1
+#endif
+constexpr int kPairGroups = RENV_PAIR_GROUPS;    // env pairs per thread (independent packed chains: ILP)
+constexpr int kPairSlots = 2 * kPairGroups;
+
 template <bool kEuler>
 __global__ void __launch_bounds__(kRolloutThreads, RENV_PAIR_CTAS)
 cartpole_rollout_pair_kernel(const __grid_constant__ RolloutArgs<float> a)
 {
-    const int64_t i0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    constexpr int S = kPairSlots;
+    const int64_t i0 = S * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
     const int64_t ld = a.env.ld, n = a.env.n;
     const int K = a.K;
     const int32_t limit = a.max_steps > 0 ? a.max_steps : 0x7fffffff;
@@ -80,7 +134,7 @@ cartpole_rollout_pair_kernel(const __grid_constant__ RolloutArgs<float> a)
     unsigned sum_r = 0, episodes = 0, viol = 0;
     float min_r = __int_as_float(0x7f800000), max_r = __int_as_float(0xff800000);
     int c = 0;                                   // packed steps executed by this thread
-    PairSlot q[2];
+    PairSlot q[S];
 
     auto deactivate = [&](PairSlot &s) { s.x = nan; s.xd = nan; s.th = nan; s.thd = nan; s.L = kInactive; };
     auto activate = [&](PairSlot &s, int steps_done, int elapsed) {
@@ -128,11 +182,12 @@ cartpole_rollout_pair_kernel(const __grid_constant__ RolloutArgs<float> a)
 
     // ---- load + step 0 (scalar: an injected state may have any angle; from step 1 on |theta| <= 0.2095) -------
     const Policy<float> policy = { a.policy.w0, a.policy.w1, a.policy.w2, a.policy.w3, a.policy.b };
-    bool term0[2] = { false, false };
+    bool term0[S];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < S; ++k) {
         PairSlot &s = q[k];
         const int64_t i = i0 + k;
+        term0[k] = false;
         s.parked = -1; s.B = 0; s.E = 0;
         s.ng = -1.0f; s.fot = 1.0f; s.pmlot = 1.0f; s.l43 = 1.0f; s.nlpm = -0.5f;
         if (i < n) {
@@ -148,71 +203,47 @@ cartpole_rollout_pair_kernel(const __grid_constant__ RolloutArgs<float> a)
     }
     c = 1;
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < S; ++k)
         if (i0 + k < n && (term0[k] || c >= q[k].L)) on_event(q[k], i0 + k, term0[k]);
 
-    // ---- packed constants -------------------------------------------------------------------------------------
-    const u64 W0 = splat(policy.w0), W1 = splat(policy.w1), W2 = splat(policy.w2), W3 = splat(policy.w3), WB = splat(policy.b);
-    const u64 C120 = splat(1.0f / 120.0f), CM6 = splat(-1.0f / 6.0f), CM720 = splat(-1.0f / 720.0f), C24 = splat(1.0f / 24.0f);
-    const u64 CMH = splat(-0.5f), ONE = splat(1.0f), TAU = splat((float)kTau), NTAU = splat(-(float)kTau);
+    const PairConsts kc = { splat(policy.w0), splat(policy.w1), splat(policy.w2), splat(policy.w3), splat(policy.b),
+                            splat(1.0f / 120.0f), splat(-1.0f / 6.0f), splat(-1.0f / 720.0f), splat(1.0f / 24.0f),
+                            splat(-0.5f), splat(1.0f), splat((float)kTau), splat(-(float)kTau) };
     const float xthr = (float)kXThreshold, ththr = (float)kThetaThreshold;
 
     for (;;) {
 #pragma unroll
         for (int u = 0; u < kStepsPerCheck; ++u) {
-            u64 X = pk(q[0].x, q[1].x), XD = pk(q[0].xd, q[1].xd), TH = pk(q[0].th, q[1].th), THD = pk(q[0].thd, q[1].thd);
-            const u64 NG = pk(q[0].ng, q[1].ng), PMLOT = pk(q[0].pmlot, q[1].pmlot), L43 = pk(q[0].l43, q[1].l43),
-                      NLPM = pk(q[0].nlpm, q[1].nlpm);
-            // policy a = [w.s + b > 0]                                   (policy_action<float>)
-            u64 acc = fma2(W0, X, WB);
-            acc = fma2(W1, XD, acc);
-            acc = fma2(W2, TH, acc);
-            acc = fma2(W3, THD, acc);
-            float acc0, acc1;
-            unpk(acc, acc0, acc1);
-            const u64 PUSH = pk(acc0 > 0.0f ? q[0].fot : -q[0].fot, acc1 > 0.0f ? q[1].fot : -q[1].fot);
-            // sin / cos                                                  (sincos_small<true>)
-            const u64 X2 = mul2(TH, TH);
-            const u64 PS = fma2(X2, C120, CM6);
-            const u64 SN = fma2(mul2(TH, X2), PS, TH);
-            u64 PC = fma2(X2, CM720, C24);
-            PC = fma2(X2, PC, CMH);
-            const u64 CS = fma2(X2, PC, ONE);
-            // dynamics<float>; NNUM = -num and NTHACC = -theta_acc (exact: rounding is sign-symmetric)
-            const u64 TEMP = fma2(mul2(mul2(THD, THD), SN), PMLOT, PUSH);
-            const u64 NNUM = fma2(NG, SN, mul2(CS, TEMP));
-            const u64 DEN = fma2(NLPM, mul2(CS, CS), L43);
-            float den0, den1;
-            unpk(DEN, den0, den1);
-            const u64 NTHACC = mul2(NNUM, pk(rcp_approx(den0), rcp_approx(den1)));
-            const u64 XACC = fma2(mul2(PMLOT, CS), NTHACC, TEMP);
-            if (kEuler) {
-                X = fma2(TAU, XD, X);
-                XD = fma2(TAU, XACC, XD);
-                TH = fma2(TAU, THD, TH);
-                THD = fma2(NTAU, NTHACC, THD);
-            } else {
-                XD = fma2(TAU, XACC, XD);
-                X = fma2(TAU, XD, X);
-                THD = fma2(NTAU, NTHACC, THD);
-                TH = fma2(TAU, THD, TH);
-            }
-            unpk(X, q[0].x, q[1].x); unpk(XD, q[0].xd, q[1].xd); unpk(TH, q[0].th, q[1].th); unpk(THD, q[0].thd, q[1].thd);
+#pragma unroll
+            for (int g = 0; g < kPairGroups; ++g) pair_step<kEuler>(q[2 * g], q[2 * g + 1], kc);
             c += 1;
-            const bool t0 = fabsf(q[0].x) > xthr || fabsf(q[0].th) > ththr;
-            const bool t1 = fabsf(q[1].x) > xthr || fabsf(q[1].th) > ththr;
-            const bool e0 = t0 || c >= q[0].L, e1 = t1 || c >= q[1].L;
-            if (e0 || e1) {
-                if (e0) on_event(q[0], i0, t0);
-                if (e1) on_event(q[1], i0 + 1, t1);
+            bool term[S], any = false;
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                term[k] = fabsf(q[k].x) > xthr || fabsf(q[k].th) > ththr;
+                any = any || term[k] || c >= q[k].L;
+            }
+            if (any) {
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+                    if (term[k] || c >= q[k].L) on_event(q[k], i0 + k, term[k]);
             }
         }
-        const unsigned p0 = __ballot_sync(0xffffffffu, q[0].parked >= 0), p1 = __ballot_sync(0xffffffffu, q[1].parked >= 0);
-        const unsigned running = __ballot_sync(0xffffffffu, q[0].L != kInactive || q[1].L != kInactive);
-        const int nparked = __popc(p0) + __popc(p1);
-        if (nparked != 0 && (nparked >= kPairResetBatch || running == 0u)) {
-            if (q[0].parked >= 0) reset_slot(q[0], i0);
-            if (q[1].parked >= 0) reset_slot(q[1], i0 + 1);
+        int nparked = 0;
+        bool active = false, parked = false;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            nparked += __popc(__ballot_sync(0xffffffffu, q[k].parked >= 0));
+            active = active || q[k].L != kInactive;
+            parked = parked || q[k].parked >= 0;
+        }
+        const unsigned running = __ballot_sync(0xffffffffu, active);
+        if (nparked != 0 && (nparked >= kPairResetBatch * kPairGroups || running == 0u)) {
+            if (parked) {
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+                    if (q[k].parked >= 0) reset_slot(q[k], i0 + k);
+            }
             continue;                       // revived slots may still have steps to do
         }
         if (running == 0u) break;
