@@ -11,8 +11,9 @@
 //
 // double: library normcdfinv / log / sincospi with explicitly rounded affine maps (parity path).
 // float:  the truncation to [-2, 2] keeps the inverse CDF in its central region, so Phi^-1 is one MUFU.LG2 and a
-//         degree-6 polynomial (no tail branches, max abs error 2.9e-7 = 1.2 ulp at |z| = 2); Box-Muller uses the
-//         MUFU log / sin / cos / rsqrt approximations (abs error ~2^-21, far below anything a DR law can resolve).
+//         degree-6 polynomial (no tail branches, no sign select, max abs error ~5e-7 at |z| = 2); Box-Muller uses the
+//         MUFU lg2 / sqrt / sin / cos approximations (abs error ~2^-21, far below anything a DR law can resolve).
+//         Both transforms start from the integer draw (r >> 8): the 2^-24 scale is folded into their first FMA.
 #pragma once
 #include "renv_philox.cuh"
 
@@ -35,19 +36,32 @@ struct DrCfg4 {
 };
 
 template <typename T> struct Num;
+// MUFU.LG2 without the denormal-input scaling of lg2.approx.f32 (3 extra instructions): arguments here are >= 0.089.
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <> struct Num<float> {
     __device__ static __forceinline__ float affine(float scale, float u, float off) { return fmaf(scale, u, off); }
     __device__ static __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    // z = Phi^-1(Phi(-2) + u * (Phi(2) - Phi(-2))), u in [0, 1).  With x = 2p - 1 in [-X, X], X = Phi(2) - Phi(-2),
-    // z = sqrt(2) erfinv(x) = x * g(w), w = -ln(1 - x^2) in [0, 2.42]; g is fitted (Chebyshev nodes, degree 6 in
-    // t = w - 1.25).  1 - |x| is formed from s = min(u, 1-u) (exact in fp32) to avoid cancellation near |z| = 2.
-    __device__ static __forceinline__ float tn_z(float u)
+    // z = Phi^-1(Phi(-2) + u * (Phi(2) - Phi(-2))) for u = (r >> 8) * 2^-24 in [0, 1).  With X = Phi(2) - Phi(-2) and
+    // x = 2p - 1 = X (2u - 1) in [-X, X):  z = sqrt(2) erfinv(x) = x * g(w), w = -ln(1 - x^2) in [0, 2.42]; g is fitted
+    // (Chebyshev nodes, degree 6 in t = w - 1.25, max abs error of z 2.9e-7).  1 - x^2 >= 0.089, so forming it with
+    // one FMA loses nothing that matters (<= 2e-7 in z).  11 FMA-pipe + 1 MUFU + 2 ALU instructions per value.
+    __device__ static __forceinline__ float tn_z_bits(uint32_t r)
     {
         const float X = (float)kPhiSpan;
-        const float s = fminf(u, __fsub_rn(1.0f, u));
-        const float a = fmaf(2.0f * X, s, 1.0f - X);              // 1 - |x|
-        const float b = __fsub_rn(2.0f, a);                        // 1 + |x|
-        const float t = fmaf(__log2f(__fmul_rn(a, b)), -0.69314718056f, -1.25f);
+        const float x = fmaf((float)(r >> 8), 2.0f * X / 16777216.0f, -X);
+        const float t = fmaf(lg2_approx(fmaf(-x, x, 1.0f)), -0.69314718056f, -1.25f);
         float g = -6.496782899e-06f;
         g = fmaf(g, t, 4.291892561e-05f);
         g = fmaf(g, t, 2.023686373e-04f);
@@ -55,19 +69,27 @@ template <> struct Num<float> {
         g = fmaf(g, t, 3.552299202e-03f);
         g = fmaf(g, t, 3.528738932e-01f);
         g = fmaf(g, t, 1.682294103e+00f);
-        const float z = __fmul_rn(g, __fsub_rn(1.0f, a));
-        return u >= 0.5f ? z : -z;
+        return __fmul_rn(g, x);
     }
-    // 4 standard normals from one Philox block: Box-Muller on the pairs (x,y) and (z,w), both branches used
+    __device__ static __forceinline__ void tn_z4(uint4 r, float z[4])
+    {
+        z[0] = tn_z_bits(r.x); z[1] = tn_z_bits(r.y); z[2] = tn_z_bits(r.z); z[3] = tn_z_bits(r.w);
+    }
+    // 4 standard normals from one Philox block: Box-Muller on the pairs (x,y) and (z,w), both branches used.
+    // radius^2 = -2 ln u1 with u1 = ((r >> 8) + 1) 2^-24 in (0, 1]  ==  (24 - lg2(k)) * 2 ln 2, k = (r >> 8) + 1;
+    // angle = 2 pi (u2 - 1/2).  MUFU lg2 / sqrt / sin / cos (abs error ~2^-21, far below what a DR law resolves).
+    __device__ static __forceinline__ void normal_pair(uint32_t ra, uint32_t rb, float *z)
+    {
+        const float two_ln2 = 1.3862943611198906f, two_pi = 6.283185307179586f;
+        const float rad = sqrt_approx(fmaf(lg2_approx((float)((ra >> 8) + 1u)), -two_ln2, 24.0f * two_ln2));
+        const float ang = fmaf((float)(rb >> 8), two_pi / 16777216.0f, -0.5f * two_pi);
+        z[0] = __fmul_rn(rad, __cosf(ang));
+        z[1] = __fmul_rn(rad, __sinf(ang));
+    }
     __device__ static __forceinline__ void normals(uint4 r, float z[4])
     {
-        const float two_pi = 6.283185307179586f;
-        float rad = __fsqrt_rn(-2.0f * __logf(u01_open0(r.x)));
-        float ang = two_pi * (u01(r.y) - 0.5f);
-        z[0] = rad * __cosf(ang); z[1] = rad * __sinf(ang);
-        rad = __fsqrt_rn(-2.0f * __logf(u01_open0(r.z)));
-        ang = two_pi * (u01(r.w) - 0.5f);
-        z[2] = rad * __cosf(ang); z[3] = rad * __sinf(ang);
+        normal_pair(r.x, r.y, z);
+        normal_pair(r.z, r.w, z + 2);
     }
 };
 template <> struct Num<double> {
@@ -78,6 +100,11 @@ template <> struct Num<double> {
     }
     __device__ static __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     __device__ static __forceinline__ double tn_z(double u) { return normcdfinv(affine(kPhiSpan, u, kPhiMinus2)); }
+    __device__ static __forceinline__ void tn_z4(uint4 r, double z[2])
+    {
+        Pack<double>::uniforms(r, z);
+        z[0] = tn_z(z[0]); z[1] = tn_z(z[1]);
+    }
     __device__ static __forceinline__ void normals(uint4 r, double z[2]) { Pack<double>::normals(r, z); }
 };
 
@@ -127,9 +154,7 @@ __device__ __forceinline__ void standard_draws(bool tn, uint64_t seed, uint64_t 
     constexpr int P = Pack<T>::kPerBlock;
     const uint4 r = draw_block(seed, id, tick, purpose, slot);
     if (tn) {
-        Pack<T>::uniforms(r, z);
-#pragma unroll
-        for (int k = 0; k < P; ++k) z[k] = Num<T>::tn_z(z[k]);
+        Num<T>::tn_z4(r, z);
     } else {
         Num<T>::normals(r, z);
     }
