@@ -415,6 +415,24 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
         del env
         torch.cuda.empty_cache()
 
+    # BASELINE configs[2]: truncnormal DR, 2^26 envs IN TOTAL sharded by index over the ranks (strong scaling), one
+    # 500-step iteration of the fused rollout + the all-gather of the return statistics (SURVEY 8d cfg 3)
+    total, K = 1 << 26, 500
+    lo_id, hi_id = renv.shard_range(total, rank, world)
+    env = renv.RandomCartPoleVecEnv(hi_id - lo_id, dtype="float32", device=dev, seed=3, env_id0=lo_id)
+    env.set_dr_distribution("truncnorm", [9.8, 0.98, 1.0, 0.1, 0.2, 0.02, 0.5, 0.05]); env.set_dr_training(True); env.reset()
+    w = (0.1, 0.1, 1.0, 0.3)
+    env.rollout(w, 0.0, 10)
+    renv.allgather_stats(env.stats_tensor)
+    env.reset_stats()
+    ms = timed(lambda: (env.rollout(w, 0.0, K), renv.allgather_stats(env.stats_tensor)))
+    st = renv.summarize_stats(renv.allgather_stats(env.stats_tensor)[0].cpu().numpy())
+    out["cfg3_truncnorm_64M_sharded_rollout"] = {"env_steps_per_s": total * K / (ms * 1e-3), "ms": ms, "envs_total": total,
+                                                 "envs_per_gpu": hi_id - lo_id, "K": K, "scaling": "strong",
+                                                 "episodes": st["episodes"], "mean_return": st["mean_return"]}
+    del env
+    torch.cuda.empty_cache()
+
     # BASELINE configs[4]: humanoid 30-dim sampler sweep, 2^24 samples per call
     nu = list(renv.HUMANOID_NOMINAL)
     n = 1 << 24
