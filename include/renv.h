@@ -147,7 +147,7 @@ int renv_cartpole_step_noisy_f64(const renv_cartpole_env *env, const renv_obs_no
                                  void *stream);
 
 /* K fused steps with the linear policy a = [w.s + b > 0] evaluated in-kernel, auto-reset always on.
- * State, xi and counters stay in registers for the K steps.  stats (device, RENV_NUM_STATS doubles,
+ * State, xi and counters stay in registers for the K steps (1 <= K <= 2^30).  stats (device, RENV_NUM_STATS doubles,
  * caller-initialised to {0,0,0,+inf,-inf,0}) is ACCUMULATED with the finished episodes' returns. */
 int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
                               int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,

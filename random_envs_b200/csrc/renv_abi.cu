@@ -228,7 +228,7 @@ int cartpole_rollout(const renv_cartpole_env *env, const double w[4], double b, 
     if (rc) return rc;
     if (w == nullptr || stats == nullptr) return RENV_E_NULL;
     if (!aligned(stats, 8)) return RENV_E_ALIGN;
-    if (K <= 0) return RENV_E_SIZE;
+    if (K <= 0 || K > (1 << 30)) return RENV_E_SIZE;      // per-thread step counters are 32-bit
     if (integrator != RENV_EULER && integrator != RENV_SEMI_IMPLICIT) return RENV_E_INTEGRATOR;
     rc = to_cfg4(dr, &a.dr);
     if (rc) return rc;
