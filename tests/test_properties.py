@@ -1,7 +1,7 @@
 """T2 property tests (hypothesis).  CPU part: host logic; GPU part: kernel invariants over random shapes/seeds."""
 import numpy as np
 import pytest
-from hypothesis import HealthCheck, given, settings, strategies as st
+from hypothesis import HealthCheck, assume, given, settings, strategies as st
 
 import random_envs_b200 as random_envs
 from oracle import c_oracle, cartpole_port as port
@@ -128,3 +128,46 @@ def _again(env_id, dr_type, distr, n, seed):
     s = random_envs.TaskSampler(env_id); s.seed_dr(seed)
     s.set_dr_distribution(dr_type, list(distr))
     return s.sample_tasks(n)
+
+
+@gpu
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.filter_too_much])
+@given(st.integers(1, 700), st.integers(1, 70), st.integers(0, 12), st.sampled_from(["float32", "float64"]),
+       st.sampled_from([(0.0, 0.0, 1.0, 0.0), (0.0, 0.0, -1.0, 0.0), (0.1, 0.1, 1.0, 0.3), (0.0, 0.0, 0.0, 0.0)]),
+       st.sampled_from([-1.0, 0.0, 1.0]), st.integers(0, 2 ** 40), st.booleans())
+def test_fused_rollout_equals_single_steps_for_any_shape(n, K, limit, dtype, w, b, seed, euler):
+    """The deferred, warp-batched resets and the packed env-pair kernel must not change a single bit: any n (odd sizes
+    leave a half-empty pair), any K (incl. K = 1 and episodes ending on the last step), any step limit (limit 1 ends
+    every episode at every step), destabilising / stabilising / constant policies."""
+    import torch
+    nz = [c for c in range(4) if w[c] != 0.0]
+    # the fp32 kernel evaluates w.s + b as an FMA chain; torch reproduces that bit for bit only for tie-free forms
+    assume(dtype == "float64" or not nz or (len(nz) == 1 and b == 0.0))
+    mk = lambda: _mk_roll(n, seed, dtype, limit, euler)
+    fused, stepped = mk(), mk()
+    fused.reset(); stepped.reset()
+    fused.rollout(w, b, K)
+    ends = 0
+    for _ in range(K):
+        s = stepped.state
+        if not nz:
+            act = torch.full((n,), int(b > 0), dtype=torch.uint8, device="cuda")
+        elif dtype == "float32":
+            act = (s[:, nz[0]] * w[nz[0]] > 0).to(torch.uint8)
+        else:                       # policy_action<double>: left-to-right, separately rounded
+            acc = s[:, 0] * w[0]
+            for c in range(1, 4):
+                acc = acc + s[:, c] * w[c]
+            act = (acc + b > 0).to(torch.uint8)
+        _, _, done, _ = stepped.step(act)
+        ends += int(done.sum())
+    assert torch.equal(fused.state, stepped.state) and torch.equal(fused.get_task(), stepped.get_task())
+    assert torch.equal(fused.elapsed, stepped.elapsed) and torch.equal(fused.episode, stepped.episode)
+    assert int(fused.stats_tensor[0]) == ends
+
+
+def _mk_roll(n, seed, dtype, limit, euler):
+    env = random_envs.RandomCartPoleVecEnv(n, dtype=dtype, seed=seed, max_episode_steps=limit,
+                                           kinematics_integrator="euler" if euler else "semi")
+    env.set_dr_distribution("uniform", [2.0, 20.0, 0.5, 3.0, 0.05, 0.3, 0.1, 1.0]); env.set_dr_training(True)
+    return env
