@@ -27,7 +27,17 @@ def require_cuda(device=None):
 
 
 def stream_ptr(device):
-    return ctypes.c_void_p(torch().cuda.current_stream(device).cuda_stream)
+    return ctypes.c_void_p(raw_stream(device.index))
+
+
+def raw_stream(device_index):
+    """cudaStream_t of torch's current stream on that device, as an int.  torch._C._cuda_getCurrentRawStream skips
+    the Stream object (0.3 us instead of 1.5 us per call -- it matters for 10 us kernels); falls back if it is gone."""
+    t = torch()
+    fast = getattr(t._C, "_cuda_getCurrentRawStream", None)
+    if fast is not None:
+        return fast(device_index)
+    return t.cuda.current_stream(device_index).cuda_stream
 
 
 def ptr(tensor):

@@ -237,11 +237,13 @@ class RandomCartPoleVecEnv(RandomEnv):
         n = self.num_envs
         fn, head = self._entry("step")
         info = {"TimeLimit.truncated": b["truncated"][:n].view(t.bool)} if self.track_truncated else {}
+        viol = self._violation_counter(b["device"])
         plan = dict(key=key, fn=getattr(_lib.load(), fn), name=fn, head=head,
                     reward=_device.ptr(b["reward"]), done=_device.ptr(b["done"]),
                     truncated=_device.ptr(b["truncated"]) if self.track_truncated else None,
                     out=(self.obs, b["reward"][:n], b["done"][:n].view(t.bool)), info=info,
-                    device_index=b["device"].index)
+                    device_index=b["device"].index, viol=ctypes.c_void_p(viol.data_ptr()), viol_tensor=viol,
+                    own_action=b["action"], own_action_ptr=_device.ptr(b["action"]))
         b["step_plan"] = plan
         return plan
 
@@ -252,15 +254,18 @@ class RandomCartPoleVecEnv(RandomEnv):
         by every step (as the reference's obs aliases its state, random_cartpole.py:224)."""
         b = self._alloc()
         t = _device.torch()
-        staged = self._stage_actions(actions)
-        viol = self._violation_counter(b["device"])
         plan = self._step_plan()
+        if actions is plan["own_action"] or actions is b.get("action_view"):   # sample_actions(): nothing to check or copy
+            action_ptr = plan["own_action_ptr"]
+        else:
+            action_ptr = ctypes.c_void_p(self._stage_actions(actions).data_ptr())
         if self.noisy:
             b["noise"].std = math.sqrt(self.noise_level)
-        args = plan["head"] + (ctypes.c_void_p(staged.data_ptr()), plan["reward"], plan["done"], plan["truncated"],
+        idx = plan["device_index"]
+        args = plan["head"] + (action_ptr, plan["reward"], plan["done"], plan["truncated"],
                                self._integrator(), self.max_episode_steps, int(self.auto_reset), self._tick,
-                               self._active_dr_cfg(), ctypes.c_void_p(viol.data_ptr()), _device.stream_ptr(b["device"]))
-        if t.cuda.current_device() == plan["device_index"]:
+                               self._active_dr_cfg(), plan["viol"], ctypes.c_void_p(_device.raw_stream(idx)))
+        if t.cuda.current_device() == idx:
             rc = plan["fn"](*args)
         else:
             with t.cuda.device(b["device"]):
@@ -271,6 +276,14 @@ class RandomCartPoleVecEnv(RandomEnv):
         obs, reward, done = plan["out"]
         return obs, reward, done, dict(plan["info"])
 
+    def _own_action_view(self):
+        """(N,) view of the env's own action buffer -- one cached object, recognised by ``step`` without any checks."""
+        b = self._buffers
+        v = b.get("action_view")
+        if v is None:
+            v = b["action_view"] = b["action"][:self.num_envs]
+        return v
+
     def sample_actions(self, out=None):
         """``action_space.sample()`` for every env: (N,) uint8 Bernoulli(1/2), Philox keyed by the step clock."""
         b = self._alloc()
@@ -279,7 +292,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         with t.cuda.device(b["device"]):
             _lib.call("renv_random_actions_u8", _device.ptr(out), self.num_envs, self.env_id0, self._seed,
                       self._tick & 0xFFFFFFFF, _device.stream_ptr(b["device"]))
-        return out[:self.num_envs] if out is b["action"] else out
+        return self._own_action_view() if out is b["action"] else out
 
     def rollout(self, w, b=0.0, num_steps=MAX_EPISODE_STEPS):
         """K fused env-steps under the in-kernel linear policy a = [w.s + b > 0] (auto-reset always on)."""
