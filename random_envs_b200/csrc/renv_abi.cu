@@ -71,6 +71,29 @@ template <typename T> int attach_noise(const renv_obs_noise *noise, EnvPtrs<T> *
 
 inline int launch_status() { return (int)cudaGetLastError(); }
 
+#ifndef RENV_STEP_PDL
+#define RENV_STEP_PDL 1
+#endif
+// Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream drains and
+// synchronises itself with griddepcontrol.wait (see cartpole_step_kernel).  Captured into CUDA graphs as a
+// programmatic dependency edge.
+template <typename Args>
+int launch_pdl(void (*kernel)(const Args), unsigned blocks, unsigned threads, cudaStream_t stream, const Args &args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = RENV_STEP_PDL ? 1 : 0;
+    const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, args);
+    return rc != cudaSuccess ? (int)rc : launch_status();
+}
+
 template <typename T>
 int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0, uint32_t call,
               unsigned long long *violations, void *stream)
@@ -186,11 +209,10 @@ int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, con
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool noisy = a.env.obs != nullptr;
     if (RENV_STEP_F32_BULK && sizeof(T) == 4 && auto_reset && !noisy) return launch_step_bulk(a, st);
-    if (auto_reset && !noisy) cartpole_step_kernel<T, true, false><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
-    else if (auto_reset) cartpole_step_kernel<T, true, true><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
-    else if (!noisy) cartpole_step_kernel<T, false, false><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
-    else cartpole_step_kernel<T, false, true><<<(unsigned)blocks, kStepThreads, 0, st>>>(a);
-    return launch_status();
+    if (auto_reset && !noisy) return launch_pdl(cartpole_step_kernel<T, true, false>, (unsigned)blocks, kStepThreads, st, a);
+    if (auto_reset) return launch_pdl(cartpole_step_kernel<T, true, true>, (unsigned)blocks, kStepThreads, st, a);
+    if (!noisy) return launch_pdl(cartpole_step_kernel<T, false, false>, (unsigned)blocks, kStepThreads, st, a);
+    return launch_pdl(cartpole_step_kernel<T, false, true>, (unsigned)blocks, kStepThreads, st, a);
 }
 
 // fp64: one env per thread.  fp32: an env PAIR per thread on the packed FFMA2 pipe (renv_rollout_pair.cuh).

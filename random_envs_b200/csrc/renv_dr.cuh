@@ -151,7 +151,6 @@ template <typename T>
 __device__ __forceinline__ void standard_draws(bool tn, uint64_t seed, uint64_t id, uint64_t tick, uint32_t purpose,
                                                uint32_t slot, T *z)
 {
-    constexpr int P = Pack<T>::kPerBlock;
     const uint4 r = draw_block(seed, id, tick, purpose, slot);
     if (tn) {
         Num<T>::tn_z4(r, z);
@@ -166,12 +165,12 @@ template <typename T>
 __device__ __forceinline__ unsigned first_attempt(int dr_type, const DimBlock<T> &blk, uint64_t seed, uint64_t id,
                                                   uint64_t tick, uint32_t purpose, int j, T *out)
 {
-    constexpr int P = Pack<T>::kPerBlock;
     unsigned pending = 0;
     if (dr_type == kDrUniform) {
         // dims beyond `dim` have a = b = 0 and are never stored by the caller
         Pack<T>::uniform_affine(draw_block(seed, id, tick, purpose, (uint32_t)j), blk.b, blk.a, out);
     } else if (dr_type == kDrTruncnorm || dr_type == kDrGaussian) {
+        constexpr int P = Pack<T>::kPerBlock;
         T z[P];
         standard_draws<T>(dr_type == kDrTruncnorm, seed, id, tick, purpose, (uint32_t)j, z);
 #pragma unroll

@@ -125,6 +125,13 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpo
     const bool live = i0 < n;
     const bool full = i0 + V <= n;
 
+    // Programmatic dependent launch (the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization): let the
+    // NEXT launch of the stream be scheduled into SM slots as this grid drains, and wait here -- before the first
+    // global access -- until the PREVIOUS grid has completed and flushed.  Back-to-back steps of one stream then
+    // lose the ~1.5 us launch/ramp gap between 11 us kernels.  Both instructions are no-ops without the attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     T s[4][V];
     Xi<T> p[V];
     int32_t el[V];
