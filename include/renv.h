@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RENV_ABI_VERSION 3
+#define RENV_ABI_VERSION 4
 #define RENV_MAX_DIM 32          /* largest task_dim in the suite is 30 (jinja/random_humanoid.py) */
 #define RENV_NUM_STATS 6         /* episodes, sum R, sum R^2, min R, max R, sum length */
 
@@ -155,6 +155,16 @@ int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], d
 int renv_cartpole_rollout_f64(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
                               int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,
                               unsigned long long *violations, void *stream);
+
+/* The same with the Noisy variant's observation model: the policy acts on obs = state + std * N(0, I) -- for the
+ * first step the content of noise->obs (what the last reset/step left there), afterwards the observation each step
+ * or reset would have returned -- and noise->obs is left as K calls of step_noisy would leave it. */
+int renv_cartpole_rollout_noisy_f32(const renv_cartpole_env *env, const renv_obs_noise *noise, const double w[4], double b,
+                                    int K, int integrator, int max_steps, uint64_t tick, const renv_dr_cfg *dr,
+                                    double *stats, unsigned long long *violations, void *stream);
+int renv_cartpole_rollout_noisy_f64(const renv_cartpole_env *env, const renv_obs_noise *noise, const double w[4], double b,
+                                    int K, int integrator, int max_steps, uint64_t tick, const renv_dr_cfg *dr,
+                                    double *stats, unsigned long long *violations, void *stream);
 
 /* action_space.sample() for n envs (test_random_policy.py:26): Bernoulli(1/2) bits of Philox block
  * (env_id >> 7, tick = step). */

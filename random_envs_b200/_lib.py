@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RENV_B200_LIB", os.path.join(_HERE, "librenv_b200.so"))   # override: kernel experiments
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_DIM = 32
 NUM_STATS = 6
 
@@ -60,6 +60,8 @@ SIGNATURES = {
     "renv_cartpole_step_noisy_f64": (_int, [_env_p, _noise_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_rollout_f32": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_cartpole_rollout_f64": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
+    "renv_cartpole_rollout_noisy_f32": (_int, [_env_p, _noise_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
+    "renv_cartpole_rollout_noisy_f64": (_int, [_env_p, _noise_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_random_actions_u8": (_int, [_vp, _i64, _u64, _u64, _u32, _vp]),
     "renv_fma_peak_f32": (_int, [_vp, _int, _int, _int, _vp]),
     "renv_fma_peak_f64": (_int, [_vp, _int, _int, _int, _vp]),

@@ -215,9 +215,19 @@ int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, con
     return launch_pdl(cartpole_step_kernel<T, false, true>, (unsigned)blocks, kStepThreads, st, a);
 }
 
+// Noisy variant (policy on the noisy observation): one env per thread for both element types.
+template <typename T> int launch_rollout_noisy(const RolloutArgs<T> &a, cudaStream_t stream)
+{
+    const int64_t blocks = (a.env.n + kRolloutThreads - 1) / kRolloutThreads;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    if (a.euler) cartpole_rollout_kernel<T, true, true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+    else cartpole_rollout_kernel<T, false, true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+    return launch_status();
+}
 // fp64: one env per thread.  fp32: an env PAIR per thread on the packed FFMA2 pipe (renv_rollout_pair.cuh).
 int launch_rollout(const RolloutArgs<double> &a, cudaStream_t stream)
 {
+    if (a.env.obs) return launch_rollout_noisy(a, stream);
     const int64_t blocks = (a.env.n + kRolloutThreads - 1) / kRolloutThreads;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
     if (a.euler) cartpole_rollout_kernel<double, true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
@@ -226,6 +236,7 @@ int launch_rollout(const RolloutArgs<double> &a, cudaStream_t stream)
 }
 int launch_rollout(const RolloutArgs<float> &a, cudaStream_t stream)
 {
+    if (a.env.obs) return launch_rollout_noisy(a, stream);
 #if RENV_ROLLOUT_F32_PAIR
     const int64_t threads = (a.env.n + kPairSlots - 1) / kPairSlots;
     const int64_t blocks = (threads + kRolloutThreads - 1) / kRolloutThreads;
@@ -242,11 +253,14 @@ int launch_rollout(const RolloutArgs<float> &a, cudaStream_t stream)
 }
 
 template <typename T>
-int cartpole_rollout(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator, int max_steps,
-                     uint64_t tick, const renv_dr_cfg *dr, double *stats, unsigned long long *violations, void *stream)
+int cartpole_rollout(const renv_cartpole_env *env, const renv_obs_noise *noise, const double w[4], double b, int K,
+                     int integrator, int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,
+                     unsigned long long *violations, void *stream)
 {
     RolloutArgs<T> a;
     int rc = check_env<T>(env, false, &a.env);
+    if (rc) return rc;
+    rc = attach_noise<T>(noise, &a.env);
     if (rc) return rc;
     if (w == nullptr || stats == nullptr) return RENV_E_NULL;
     if (!aligned(stats, 8)) return RENV_E_ALIGN;
@@ -365,13 +379,28 @@ int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], d
                               int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,
                               unsigned long long *violations, void *stream)
 {
-    return cartpole_rollout<float>(env, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
+    return cartpole_rollout<float>(env, nullptr, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
 }
 int renv_cartpole_rollout_f64(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
                               int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,
                               unsigned long long *violations, void *stream)
 {
-    return cartpole_rollout<double>(env, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
+    return cartpole_rollout<double>(env, nullptr, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
+}
+
+int renv_cartpole_rollout_noisy_f32(const renv_cartpole_env *env, const renv_obs_noise *noise, const double w[4], double b,
+                                    int K, int integrator, int max_steps, uint64_t tick, const renv_dr_cfg *dr,
+                                    double *stats, unsigned long long *violations, void *stream)
+{
+    if (noise == nullptr) return RENV_E_NULL;
+    return cartpole_rollout<float>(env, noise, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
+}
+int renv_cartpole_rollout_noisy_f64(const renv_cartpole_env *env, const renv_obs_noise *noise, const double w[4], double b,
+                                    int K, int integrator, int max_steps, uint64_t tick, const renv_dr_cfg *dr,
+                                    double *stats, unsigned long long *violations, void *stream)
+{
+    if (noise == nullptr) return RENV_E_NULL;
+    return cartpole_rollout<double>(env, noise, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
 }
 
 int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step, void *stream)

@@ -356,6 +356,10 @@ template <typename T> struct RolloutThread {
     int remaining;      // steps this lane may still execute now (0 while parked or finished)
     int parked;         // steps left after the pending reset, -1 when not parked
     uint64_t reset_tick;
+    // Noisy variant only: the observation the policy sees at the next step.  Either the one found in the obs buffer
+    // at launch (obs_loaded), or state + std * N(0,I) keyed by the tick that produced the state and `after_reset`
+    // (0: a step's observation, 1: a reset's) -- exactly what step() / reset() wrote for that tick.
+    State<T> obs0; bool obs_loaded; uint32_t after_reset;
     unsigned long long sum_r2; unsigned sum_r; float min_r, max_r; unsigned episodes, sum_len, viol;
 };
 
@@ -375,11 +379,24 @@ constexpr int kUnrollF64 = RENV_UNROLL_F64;
 #define RENV_ROLLOUT_F64_CTAS 3
 #endif
 
-template <typename T, bool kEuler, bool kKnownSmall>
+template <typename T, bool kEuler, bool kKnownSmall, bool kNoisy = false>
 __device__ __forceinline__ void rollout_step(RolloutThread<T> &t, const RolloutArgs<T> &a, const Policy<T> &policy,
-                                             int32_t limit)
+                                             int32_t limit, uint64_t id = 0)
 {
-    const int action = policy_action(policy, t.s);
+    int action;
+    if (kNoisy) {       // the policy acts on the OBSERVATION of the current state (what step()/reset() returned for it)
+        State<T> o = t.obs0;
+        if (!t.obs_loaded) {
+            T ov[4];
+            const uint64_t tick_now = a.tick + (uint64_t)(a.K - t.remaining);
+            add_obs_noise(t.s, a.env.noise_std, a.env.seed, id, tick_now - 1, t.after_reset, ov);
+            o = State<T>{ ov[0], ov[1], ov[2], ov[3] };
+        }
+        t.obs_loaded = false; t.after_reset = 0u;
+        action = policy_action(policy, o);
+    } else {
+        action = policy_action(policy, t.s);
+    }
     const bool terminated = dynamics<kKnownSmall>(t.s, t.p, t.d, action, kEuler);
     t.el += 1;
     if (terminated || t.el >= limit) {
@@ -405,6 +422,7 @@ __device__ __forceinline__ void rollout_reset(RolloutThread<T> &t, const Rollout
         t.xi_dirty = true;
     }
     init_state(t.s, a.env.seed, id, t.reset_tick);
+    t.after_reset = 1u;
     t.remaining = t.parked;
     t.parked = -1;
 }
@@ -414,7 +432,7 @@ __device__ __forceinline__ void rollout_reset(RolloutThread<T> &t, const Rollout
 __device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
 __device__ __forceinline__ double pin(double v) { asm volatile("" : "+d"(v)); return v; }
 
-template <typename T, bool kEuler>
+template <typename T, bool kEuler, bool kNoisy = false>
 __global__ void __launch_bounds__(kRolloutThreads, (sizeof(T) == 4 ? 3 : RENV_ROLLOUT_F64_CTAS))
 cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 {
@@ -433,6 +451,9 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
     t.d = derive(t.p);
     t.el = a.env.elapsed[il];
     t.new_episodes = 0; t.xi_dirty = false; t.parked = -1; t.reset_tick = 0;
+    t.obs_loaded = kNoisy; t.after_reset = 0u;
+    if (kNoisy) t.obs0 = State<T>{ a.env.obs[il], a.env.obs[ld + il], a.env.obs[2 * ld + il], a.env.obs[3 * ld + il] };
+    else t.obs0 = t.s;
     const uint64_t id = a.env.env_id0 + (uint64_t)il;
     const int32_t limit = a.max_steps > 0 ? a.max_steps : 0x7fffffff;
     t.remaining = live ? a.K : 0;
@@ -440,16 +461,16 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 
     // Step 0 may start from a user-injected state with any angle; from step 1 on |theta| <= 0.2095 holds at
     // every step start (an env beyond the threshold was just reset), so the sin/cos range check is dropped.
-    if (t.remaining > 0) rollout_step<T, kEuler, false>(t, a, policy, limit);
+    if (t.remaining > 0) rollout_step<T, kEuler, false, kNoisy>(t, a, policy, limit, id);
     for (;;) {
-        if (sizeof(T) == 4) {
+        if (sizeof(T) == 4 && !kNoisy) {
 #pragma unroll
             for (int u = 0; u < kStepsPerCheck; ++u)
-                if (t.remaining > 0) rollout_step<T, kEuler, true>(t, a, policy, limit);
-        } else {            // the fp64 step is ~10x the code of the fp32 one: keep the loop body inside the i-cache
+                if (t.remaining > 0) rollout_step<T, kEuler, true, kNoisy>(t, a, policy, limit, id);
+        } else {            // the fp64 / noisy step is ~10x the code of the fp32 one: keep the loop body inside the i-cache
 #pragma unroll kUnrollF64
             for (int u = 0; u < kStepsPerCheck; ++u)
-                if (t.remaining > 0) rollout_step<T, kEuler, true>(t, a, policy, limit);
+                if (t.remaining > 0) rollout_step<T, kEuler, true, kNoisy>(t, a, policy, limit, id);
         }
         const unsigned parked = __ballot_sync(0xffffffffu, t.parked >= 0);
         const unsigned running = __ballot_sync(0xffffffffu, t.remaining > 0);
@@ -466,6 +487,11 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
         if (t.xi_dirty) store_xi(a.env.xi, i, t.p);
         a.env.elapsed[i] = t.el;
         if (a.env.episode && t.new_episodes) a.env.episode[i] += t.new_episodes;
+        if (kNoisy) {       // leave the obs buffer as K calls of step() would: the observation of the last step / reset
+            T ov[4];
+            add_obs_noise(t.s, a.env.noise_std, a.env.seed, id, a.tick + (uint64_t)(a.K - 1), t.after_reset, ov);
+            a.env.obs[i] = ov[0]; a.env.obs[ld + i] = ov[1]; a.env.obs[2 * ld + i] = ov[2]; a.env.obs[3 * ld + i] = ov[3];
+        }
     }
     rollout_publish(a.stats, a.violations, t.episodes, t.sum_len, t.sum_r, t.sum_r2, t.min_r, t.max_r, t.viol);
 }

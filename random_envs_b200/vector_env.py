@@ -298,13 +298,11 @@ class RandomCartPoleVecEnv(RandomEnv):
         """K fused env-steps under the in-kernel linear policy a = [w.s + b > 0] (auto-reset always on)."""
         buf = self._alloc()
         t = _device.torch()
-        if self.noisy:
-            raise NotImplementedError("the fused rollout evaluates its policy on the true state; step() the Noisy "
-                                      "variant instead")
         w_arr = (ctypes.c_double * 4)(*[float(v) for v in w])
         viol = self._violation_counter(buf["device"])
+        fn, head = self._entry("rollout")         # Noisy variant: the policy acts on the noisy observation
         with t.cuda.device(buf["device"]):
-            _lib.call("renv_cartpole_rollout_" + self._suffix(), ctypes.byref(buf["env"]), w_arr, float(b),
+            _lib.call(fn, *head, w_arr, float(b),
                       int(num_steps), self._integrator(), self.max_episode_steps, self._tick, self._active_dr_cfg(),
                       _device.ptr(buf["stats"]), _device.ptr(viol), _device.stream_ptr(buf["device"]))
         self._tick += int(num_steps)

@@ -90,6 +90,9 @@ def test_cartpole_kernels_stay_inside_their_buffers(dtype, n):
             _lib.call("renv_cartpole_rollout_" + suffix, ctypes.byref(env), w, 0.0, K, _lib.EULER, 11, tick + 1,
                       ctypes.byref(cfg), p(stats), p(viol), stream)
             tick += K
+            _lib.call("renv_cartpole_rollout_noisy_" + suffix, ctypes.byref(env), ctypes.byref(noise), w, 0.0, K, _lib.SEMI_IMPLICIT,
+                      11, tick + 1, ctypes.byref(cfg), p(stats), p(viol), stream)
+            tick += K
     torch.cuda.synchronize()
     ar.check()
     assert bool(torch.isfinite(state.view(4, ld)[:, :n]).all()) and bool((elapsed[:n] >= 0).all())

@@ -97,8 +97,6 @@ def test_noise_level_zero_and_attribute_update():
     a = clean.sample_actions().clone()
     d = _np(noisy.step(a)[0]) - _np(clean.step(a)[0])
     assert 0.15 < d.std() < 0.25
-    with pytest.raises(NotImplementedError):
-        noisy.rollout((0.1, 0.1, 1.0, 0.3), 0.0, 4)
 
 
 def test_noisy_dropin_id_and_host_buffer_path():
@@ -123,3 +121,34 @@ def test_noisy_dropin_id_and_host_buffer_path():
         o, r, d, _ = dev.step(a)
         ho, hr, hd, _ = host.step_host(_np(a))
         assert np.array_equal(ho, _np(o)) and np.array_equal(hd, _np(d))
+
+
+@pytest.mark.parametrize("dtype,w", [("float32", (0.0, 0.0, 1.0, 0.0)), ("float64", (0.1, 0.1, 1.0, 0.3)),
+                                     ("float64", (0.0, 0.0, 1.0, 0.0))])
+@pytest.mark.parametrize("n,K,limit", [(1, 5, 500), (777, 60, 500), (4099, 33, 7)])
+def test_noisy_fused_rollout_equals_noisy_steps_with_the_policy_on_the_observation(dtype, w, n, K, limit):
+    """In the Noisy variant the in-kernel policy sees what step()/reset() returned (state + noise), not the state:
+    K fused steps == K step() calls driven by a = [w . obs > 0], bit for bit, including the obs buffer left behind."""
+    mk = lambda: random_envs.RandomCartPoleVecEnv(n, dtype=dtype, seed=31, noisy=True, noise_level=4e-4, max_episode_steps=limit)
+    fused, stepped = mk(), mk()
+    for e in (fused, stepped):
+        e.set_dr_distribution("uniform", SEARCH); e.set_dr_training(True)
+    obs = stepped.reset().clone(); fused.reset()
+    for _ in range(3):                                        # start the rollout from a mix of episode ages
+        a = stepped.sample_actions().clone()
+        obs = stepped.step(a)[0]; fused.step(a)
+    fused.rollout(w, 0.0, K)
+    for _ in range(K):
+        if dtype == "float32":
+            act = (obs[:, 2] * w[2] > 0).to(torch.uint8)      # tie-free single-weight policy: torch == FMA chain
+        else:
+            acc = obs[:, 0] * w[0]
+            for c in range(1, 4):
+                acc = acc + obs[:, c] * w[c]
+            act = (acc + 0.0 > 0).to(torch.uint8)
+        obs = stepped.step(act)[0]
+    assert torch.equal(fused.state, stepped.state) and torch.equal(fused.obs, stepped.obs)
+    assert torch.equal(fused.get_task(), stepped.get_task()) and torch.equal(fused.elapsed, stepped.elapsed)
+    assert torch.equal(fused.episode, stepped.episode)
+    differs = (fused.obs - fused.state).abs().max()
+    assert 0 < float(differs) < 0.2
