@@ -417,7 +417,7 @@ class RandomCartPoleVecEnv(RandomEnv):
     # ---- checkpoint / resume --------------------------------------------------------------------------
     def state_dict(self):
         b = self._alloc()
-        keys = ("state", "xi", "elapsed", "episode", "beyond", "stats")
+        keys = ("state", "xi", "elapsed", "episode", "beyond", "stats") + (("obs",) if self.noisy else ())
         out = {k: b[k].clone() for k in keys}
         out.update(seed=self._seed, env_id0=self.env_id0, tick=self._tick, num_envs=self.num_envs,
                    dtype=self._dtype_name)
@@ -427,7 +427,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         if sd["num_envs"] != self.num_envs or sd["dtype"] != self._dtype_name:
             raise ValueError("state_dict is for %d %s envs" % (sd["num_envs"], sd["dtype"]))
         b = self._alloc()
-        for k in ("state", "xi", "elapsed", "episode", "beyond", "stats"):
+        for k in ("state", "xi", "elapsed", "episode", "beyond", "stats") + (("obs",) if self.noisy else ()):
             b[k].copy_(sd[k])
         self._seed, self.env_id0, self._tick = sd["seed"], sd["env_id0"], sd["tick"]
         self._refresh_env_struct()

@@ -152,3 +152,21 @@ def test_noisy_fused_rollout_equals_noisy_steps_with_the_policy_on_the_observati
     assert torch.equal(fused.episode, stepped.episode)
     differs = (fused.obs - fused.state).abs().max()
     assert 0 < float(differs) < 0.2
+
+
+def test_noisy_checkpoint_resume_is_exact():
+    """state_dict carries the observation buffer: a resumed noisy env continues bit for bit (the first fused step of
+    a rollout acts on the stored observation)."""
+    mk = lambda seed: random_envs.RandomCartPoleVecEnv(1031, dtype="float32", seed=seed, noisy=True, noise_level=1e-3)
+    env = mk(17)
+    env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True)
+    env.reset()
+    for _ in range(5):
+        env.step(env.sample_actions())
+    sd = env.state_dict()
+    twin = mk(999); twin.set_dr_distribution("uniform", SEARCH); twin.set_dr_training(True)
+    twin.load_state_dict(sd)
+    for e in (env, twin):
+        e.rollout((0.0, 0.0, 1.0, 0.0), 0.0, 40)
+        e.step(e.sample_actions())
+    assert torch.equal(env.obs, twin.obs) and torch.equal(env.state, twin.state) and torch.equal(env.episode, twin.episode)
