@@ -499,10 +499,6 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 // ------------------------------------------------------------------------------------------------
 // RandomEnv.sample_tasks(n) -> (n, dim) row-major, dim <= 32
 // ------------------------------------------------------------------------------------------------
-// A CTA produces kTileSamples consecutive samples.  Work item = (sample, dim block of 4 floats / 2
-// doubles = one Philox call); values go to a shared-memory tile that is contiguous in the output, so
-// the tile is written back with fully coalesced 128-bit stores whatever `dim` is (30 is not a
-// multiple of 4: a thread-per-sample store would touch 32 sectors per instruction).
 constexpr int kSampleThreads = 256;
 // Samples per CTA: every thread produces kItemsPerThread work items whatever `dim` is (dim 30: 256 float / 128 double
 // samples; dim 4: 2048 / 1024), so the per-thread set-up (12 parameter conversions) is amortised for the 3..4-dim
