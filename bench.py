@@ -363,6 +363,21 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
         del env, a
         torch.cuda.empty_cache()
 
+    # ONE 2^20-env batch stepped repeatedly (what a single training loop does): its 62 MB working set stays in the
+    # 126 MB L2, so this is NOT an HBM number -- reported beside the headline, which rotates 4 batches to defeat L2
+    n = 1 << 20
+    env = renv.RandomCartPoleVecEnv(n, dtype="float32", device=dev, seed=1, env_id0=rank * n, track_truncated=False, track_episodes=False)
+    env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True); env.reset()
+    a = env.sample_actions().clone()
+    for _ in range(20):
+        env.step(a)
+    ms = timed(lambda: [env.step(a) for _ in range(400)])
+    out["step_f32_1M_single_batch_l2_resident"] = {"env_steps_per_s": agg(n * 400, ms), "launch_us": 1e3 * ms / 400,
+                                                   "algorithmic_gbs_per_gpu": 62 * n * 400 / (ms * 1e-3) / 1e9,
+                                                   "note": "L2-resident working set; eager step() loop on one stream"}
+    del env, a
+    torch.cuda.empty_cache()
+
     # Noisy variant: +16 B/env-step for the separate obs rows, one Philox block + Box-Muller per env
     n = 1 << 24
     env = renv.RandomCartPoleVecEnv(n, dtype="float32", device=dev, seed=1, env_id0=rank * n, track_truncated=False,
