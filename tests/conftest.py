@@ -16,6 +16,14 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+try:        # property tests: same examples on every run, no example database written into the tree
+    from hypothesis import settings as _hyp_settings
+    _hyp_settings.register_profile("repo", derandomize=True, database=None, deadline=None)
+    _hyp_settings.load_profile("repo")
+except ImportError:  # pragma: no cover
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "reference: needs /root/reference mounted (build container only)")
