@@ -125,11 +125,10 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpo
     const bool live = i0 < n;
     const bool full = i0 + V <= n;
 
-    // Programmatic dependent launch (the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization): let the
-    // NEXT launch of the stream be scheduled into SM slots as this grid drains, and wait here -- before the first
-    // global access -- until the PREVIOUS grid has completed and flushed.  Back-to-back steps of one stream then
-    // lose the ~1.5 us launch/ramp gap between 11 us kernels.  Both instructions are no-ops without the attribute.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Programmatic dependent launch (the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization): wait here
+    // -- before the first global access -- until the PREVIOUS grid of the stream has completed and flushed; further
+    // down this grid lets the NEXT one be scheduled into SM slots as it drains.  Back-to-back steps of one stream
+    // then lose most of the ~1.5 us launch/ramp gap between 11 us kernels.  No-ops without the attribute.
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     T s[4][V];
@@ -209,6 +208,11 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpo
             }
         }
 
+        // Trigger AFTER the arithmetic: the dependent grid becomes launchable when every CTA of this one is about
+        // to store, so its CTAs spin in griddepcontrol.wait only briefly.  Triggering at kernel entry was 4 % faster
+        // for one stream (eager 7.9e10 vs 7.6e10 env-steps/s) but cost the 4-independent-batch graph 1 % (0.907 vs
+        // 0.916 of the HBM peak): the early-resident waiters took SM slots from the other batches' kernels.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (full) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) vstore<typename VT::Real>(a.env.state + c * ld + i0, s[c]);
