@@ -406,8 +406,9 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
     out["fma_peak_tflops"] = peaks
 
     # BASELINE configs[3]: fused 500-step rollout, 2^24 envs per GPU, linear policy, + the stats all-gather
+    # (w = None: the random policy of BASELINE configs[0] / test_random_policy.py, one Philox block per env-step)
     for label, dtype, w in (("rollout_f32_survive", "float32", (0.1, 0.1, 1.0, 0.3)), ("rollout_f32_resetheavy", "float32", (0.0, 0.0, 1.0, 0.0)),
-                            ("rollout_f64_survive", "float64", (0.1, 0.1, 1.0, 0.3))):
+                            ("rollout_f64_survive", "float64", (0.1, 0.1, 1.0, 0.3)), ("rollout_f32_random_policy", "float32", None)):
         n, K = 1 << 24, 500
         env = renv.RandomCartPoleVecEnv(n, dtype=dtype, device=dev, seed=2, env_id0=rank * n)
         env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True); env.reset()
@@ -423,7 +424,7 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
         st = renv.summarize_stats(renv.allgather_stats(env.stats_tensor)[0].cpu().numpy())
         rate = agg(n * K, ms)
         pk = peaks["f32" if dtype == "float32" else "f64"]
-        out[label] = {"env_steps_per_s": rate, "ms": ms, "envs_per_gpu": n, "K": K, "policy_w": list(w),
+        out[label] = {"env_steps_per_s": rate, "ms": ms, "envs_per_gpu": n, "K": K, "policy_w": list(w) if w else "random",
                       "algorithmic_tflops_per_gpu": rate / world * FLOPS_PER_STEP_ROLLOUT / 1e12,
                       "frac_of_fma_peak": rate / world * FLOPS_PER_STEP_ROLLOUT / 1e12 / pk,
                       "episodes": st["episodes"], "mean_return": st["mean_return"]}

@@ -147,7 +147,9 @@ int renv_cartpole_step_noisy_f64(const renv_cartpole_env *env, const renv_obs_no
                                  void *stream);
 
 /* K fused steps with the linear policy a = [w.s + b > 0] evaluated in-kernel, auto-reset always on.
- * State, xi and counters stay in registers for the K steps (1 <= K <= 2^30).  stats (device, RENV_NUM_STATS doubles,
+ * State, xi and counters stay in registers for the K steps (1 <= K <= 2^30).  w == NULL selects the RANDOM policy
+ * of the reference's demo loop (test_random_policy.py:26): at tick t env e takes the action bit renv_random_actions_u8
+ * would give it for step = t, so the launch equals K x { renv_random_actions_u8; renv_cartpole_step } bit for bit.  stats (device, RENV_NUM_STATS doubles,
  * caller-initialised to {0,0,0,+inf,-inf,0}) is ACCUMULATED with the finished episodes' returns. */
 int renv_cartpole_rollout_f32(const renv_cartpole_env *env, const double w[4], double b, int K, int integrator,
                               int max_steps, uint64_t tick, const renv_dr_cfg *dr, double *stats,

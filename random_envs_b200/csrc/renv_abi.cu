@@ -215,6 +215,15 @@ int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, con
     return launch_pdl(cartpole_step_kernel<T, false, true>, (unsigned)blocks, kStepThreads, st, a);
 }
 
+// Random policy (w == NULL): one env per thread, one Philox block per env-step for the action bit.
+template <typename T> int launch_rollout_random(const RolloutArgs<T> &a, cudaStream_t stream)
+{
+    const int64_t blocks = (a.env.n + kRolloutThreads - 1) / kRolloutThreads;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    if (a.euler) cartpole_rollout_kernel<T, true, false, true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+    else cartpole_rollout_kernel<T, false, false, true><<<(unsigned)blocks, kRolloutThreads, 0, stream>>>(a);
+    return launch_status();
+}
 // Noisy variant (policy on the noisy observation): one env per thread for both element types.
 template <typename T> int launch_rollout_noisy(const RolloutArgs<T> &a, cudaStream_t stream)
 {
@@ -262,19 +271,21 @@ int cartpole_rollout(const renv_cartpole_env *env, const renv_obs_noise *noise, 
     if (rc) return rc;
     rc = attach_noise<T>(noise, &a.env);
     if (rc) return rc;
-    if (w == nullptr || stats == nullptr) return RENV_E_NULL;
+    if (stats == nullptr) return RENV_E_NULL;
+    if (w == nullptr && noise != nullptr) return RENV_E_ARG;      // the random policy does not look at observations
     if (!aligned(stats, 8)) return RENV_E_ALIGN;
     if (K <= 0 || K > (1 << 30)) return RENV_E_SIZE;      // per-thread step counters are 32-bit
     if (integrator != RENV_EULER && integrator != RENV_SEMI_IMPLICIT) return RENV_E_INTEGRATOR;
     rc = to_cfg4(dr, &a.dr);
     if (rc) return rc;
-    a.policy = Policy<T>{ (T)w[0], (T)w[1], (T)w[2], (T)w[3], (T)b };
+    a.policy = w ? Policy<T>{ (T)w[0], (T)w[1], (T)w[2], (T)w[3], (T)b } : Policy<T>{ T(0), T(0), T(0), T(0), T(0) };
     a.K = K;
     a.euler = integrator == RENV_EULER;
     a.max_steps = max_steps;
     a.tick = tick;
     a.stats = stats;
     a.violations = violations;
+    if (w == nullptr) return launch_rollout_random(a, static_cast<cudaStream_t>(stream));
     return launch_rollout(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -383,12 +383,24 @@ constexpr int kUnrollF64 = RENV_UNROLL_F64;
 #define RENV_ROLLOUT_F64_CTAS 3
 #endif
 
-template <typename T, bool kEuler, bool kKnownSmall, bool kNoisy = false>
+// Bernoulli(1/2) action of env `id` at clock `tick`: bit (id & 127) of Philox block (id >> 7, tick) -- the bit
+// random_actions_kernel writes for that env and tick, so a random-policy rollout equals K x step(sample_actions()).
+__device__ __forceinline__ int random_action(uint64_t seed, uint64_t id, uint64_t tick)
+{
+    const uint4 r = draw_block(seed, id >> 7, tick & 0xffffffffull, kAction, 0);
+    const uint32_t sel = (uint32_t)(id >> 5) & 3u;
+    const uint32_t word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+    return (int)((word >> (id & 31)) & 1u);
+}
+
+template <typename T, bool kEuler, bool kKnownSmall, bool kNoisy = false, bool kRandom = false>
 __device__ __forceinline__ void rollout_step(RolloutThread<T> &t, const RolloutArgs<T> &a, const Policy<T> &policy,
                                              int32_t limit, uint64_t id = 0)
 {
     int action;
-    if (kNoisy) {       // the policy acts on the OBSERVATION of the current state (what step()/reset() returned for it)
+    if (kRandom) {      // action_space.sample() of the reference's demo loop (test_random_policy.py:26), per env and tick
+        action = random_action(a.env.seed, id, a.tick + (uint64_t)(a.K - t.remaining));
+    } else if (kNoisy) {       // the policy acts on the OBSERVATION of the current state (what step()/reset() returned for it)
         State<T> o = t.obs0;
         if (!t.obs_loaded) {
             T ov[4];
@@ -436,7 +448,7 @@ __device__ __forceinline__ void rollout_reset(RolloutThread<T> &t, const Rollout
 __device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); return v; }
 __device__ __forceinline__ double pin(double v) { asm volatile("" : "+d"(v)); return v; }
 
-template <typename T, bool kEuler, bool kNoisy = false>
+template <typename T, bool kEuler, bool kNoisy = false, bool kRandom = false>
 __global__ void __launch_bounds__(kRolloutThreads, (sizeof(T) == 4 ? 3 : RENV_ROLLOUT_F64_CTAS))
 cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 {
@@ -465,16 +477,16 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 
     // Step 0 may start from a user-injected state with any angle; from step 1 on |theta| <= 0.2095 holds at
     // every step start (an env beyond the threshold was just reset), so the sin/cos range check is dropped.
-    if (t.remaining > 0) rollout_step<T, kEuler, false, kNoisy>(t, a, policy, limit, id);
+    if (t.remaining > 0) rollout_step<T, kEuler, false, kNoisy, kRandom>(t, a, policy, limit, id);
     for (;;) {
-        if (sizeof(T) == 4 && !kNoisy) {
+        if (sizeof(T) == 4 && !kNoisy && !kRandom) {
 #pragma unroll
             for (int u = 0; u < kStepsPerCheck; ++u)
-                if (t.remaining > 0) rollout_step<T, kEuler, true, kNoisy>(t, a, policy, limit, id);
+                if (t.remaining > 0) rollout_step<T, kEuler, true, kNoisy, kRandom>(t, a, policy, limit, id);
         } else {            // the fp64 / noisy step is ~10x the code of the fp32 one: keep the loop body inside the i-cache
 #pragma unroll kUnrollF64
             for (int u = 0; u < kStepsPerCheck; ++u)
-                if (t.remaining > 0) rollout_step<T, kEuler, true, kNoisy>(t, a, policy, limit, id);
+                if (t.remaining > 0) rollout_step<T, kEuler, true, kNoisy, kRandom>(t, a, policy, limit, id);
         }
         const unsigned parked = __ballot_sync(0xffffffffu, t.parked >= 0);
         const unsigned running = __ballot_sync(0xffffffffu, t.remaining > 0);

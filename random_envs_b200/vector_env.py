@@ -295,10 +295,16 @@ class RandomCartPoleVecEnv(RandomEnv):
         return self._own_action_view() if out is b["action"] else out
 
     def rollout(self, w, b=0.0, num_steps=MAX_EPISODE_STEPS):
-        """K fused env-steps under the in-kernel linear policy a = [w.s + b > 0] (auto-reset always on)."""
+        """K fused env-steps under the in-kernel linear policy a = [w.s + b > 0] (auto-reset always on), or, with
+        ``w=None``, under the random policy ``action_space.sample()`` (test_random_policy.py:26)."""
         buf = self._alloc()
         t = _device.torch()
-        w_arr = (ctypes.c_double * 4)(*[float(v) for v in w])
+        if w is None:         # random policy: the fused equivalent of K x step(sample_actions())
+            if self.noisy:
+                raise ValueError("the random policy ignores observations: use a noise-free env")
+            w_arr = None
+        else:
+            w_arr = (ctypes.c_double * 4)(*[float(v) for v in w])
         viol = self._violation_counter(buf["device"])
         fn, head = self._entry("rollout")         # Noisy variant: the policy acts on the noisy observation
         with t.cuda.device(buf["device"]):

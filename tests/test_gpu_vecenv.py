@@ -325,3 +325,25 @@ def test_dropin_timelimit_wrapper_truncates_at_500():
         if k < 499:
             assert not done
     assert done and info["TimeLimit.truncated"] is True
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("n,K,limit", [(1, 9, 500), (1000, 130, 500), (4099, 77, 11), (300, 600, 500)])
+def test_random_policy_rollout_equals_step_with_sample_actions(dtype, n, K, limit):
+    """rollout(w=None): the reference's demo loop (test_random_policy.py:25-32: action_space.sample(), reset on done)
+    fused into one launch == K x step(sample_actions()), bit for bit (env ids beyond one 128-env Philox block too)."""
+    mk = lambda: random_envs.RandomCartPoleVecEnv(n, dtype=dtype, seed=12, env_id0=(1 << 33) + 77, max_episode_steps=limit)
+    fused, stepped = mk(), mk()
+    for e in (fused, stepped):
+        e.set_dr_distribution("uniform", SEARCH); e.set_dr_training(True); e.reset()
+    fused.rollout(None, 0.0, K)
+    ends = 0
+    for _ in range(K):
+        _, _, done, _ = stepped.step(stepped.sample_actions())
+        ends += int(done.sum())
+    assert torch.equal(fused.obs, stepped.obs) and torch.equal(fused.get_task(), stepped.get_task())
+    assert torch.equal(fused.elapsed, stepped.elapsed) and torch.equal(fused.episode, stepped.episode)
+    st = fused.episode_stats()
+    assert st["episodes"] == ends
+    if n >= 1000 and limit == 500:
+        assert 15 < st["mean_return"] < 40                    # random policy over the search bounds: ~27 steps (SURVEY 6)
