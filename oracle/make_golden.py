@@ -18,6 +18,10 @@ Files written
   sampler_reference_draws.npz  iid draws of the reference's own sample_task (uniform, gaussian,
                                truncnorm incl. a lower-bound point-mass case, fullgaussian with clipping)
                                for two-sample KS
+  cartpole_episode_lengths.npz the reference's own demo loop (test_random_policy.py:25-32: action_space.sample(),
+                               reset on done) under uniform DR over the search bounds, resampled at every reset through
+                               the reference's set_random_task: 20 000 episode lengths (both integrators) -- the
+                               end-to-end law of dynamics + termination + reset + DR, for two-sample KS against the GPU
 """
 import json
 import os
@@ -196,6 +200,33 @@ def sampler_reference_draws(n=4000):
     return out
 
 
+def episode_lengths(n_episodes=20000, seed=2024):
+    """Unmodified reference classes end to end: env.set_random_task() (its own sample_task on numpy's global state),
+    env.reset() (its own np_random), env.step(action_space.sample()) until done; TimeLimit(500) as gym.make adds."""
+    out = {}
+    for integ in ("euler", "semi-implicit-euler"):
+        env = rl.make_cartpole()
+        env.kinematics_integrator = integ
+        env.seed(seed)
+        env.action_space.seed(seed)
+        np.random.seed(seed)
+        env.set_dr_distribution("uniform", SEARCH)
+        env.set_dr_training(True)
+        lens = np.zeros(n_episodes, np.int16)
+        for e in range(n_episodes):
+            env.set_random_task()          # README.md:9 behaviour; CartPole's own reset forgets it (SURVEY 0.5)
+            env.reset()
+            T = 0
+            while True:
+                _, _, d, _ = env.step(env.action_space.sample())
+                T += 1
+                if d or T >= 500:
+                    break
+            lens[e] = T
+        out["euler" if integ == "euler" else "semi_implicit"] = lens
+    return out
+
+
 def main():
     assert rl.available(), "reference not mounted"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -207,6 +238,7 @@ def main():
     with open(os.path.join(GOLDEN, "sampler_control_flow.json"), "w") as f:
         json.dump(sampler_control_flow(), f, indent=1)
     np.savez_compressed(os.path.join(GOLDEN, "sampler_reference_draws.npz"), **sampler_reference_draws())
+    np.savez_compressed(os.path.join(GOLDEN, "cartpole_episode_lengths.npz"), **episode_lengths())
     for name in sorted(os.listdir(GOLDEN)):
         print(name, os.path.getsize(os.path.join(GOLDEN, name)))
 

@@ -144,3 +144,38 @@ def test_cfg5_sixteen_million_humanoid_samples_moments_and_support(dr_type):
     s2 = random_envs.TaskSampler("RandomHumanoid-v0"); s2.seed_dr(12); s2.set_dr_distribution(dr_type, list(distr))
     assert torch.equal(s2.sample_tasks_tensor(n, dtype=torch.float32), x)
     s.check_dr_violations()
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("integrator,key", [("euler", "euler"), ("semi-implicit-euler", "semi_implicit")])
+def test_episode_length_law_matches_the_live_references_demo_loop(golden_dir, dtype, integrator, key):
+    """End to end: dynamics + termination + TimeLimit + reset + uniform DR resample under a random policy.  The golden
+    file holds 20 000 episode lengths produced by the UNMODIFIED reference classes running their own demo loop
+    (oracle/make_golden.py: set_random_task / reset / step(action_space.sample())); the RNG streams differ, so the
+    comparison is distributional: two-sample KS at alpha = 0.001 plus mean and variance within 5 standard errors."""
+    import os
+    ref = np.load(os.path.join(golden_dir, "cartpole_episode_lengths.npz"))[key].astype(np.float64)
+    n = 1 << 17
+    env = random_envs.RandomCartPoleVecEnv(n, dtype=dtype, seed=77, kinematics_integrator=integrator)
+    env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True)
+    env.reset()
+    first = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for k in range(500):
+        el = env.elapsed.clone()
+        _, _, done, _ = env.step(env.sample_actions())
+        newly = done & (first == 0)
+        first[newly] = el[newly] + 1
+        if bool((first > 0).all()):
+            break
+    got = first.cpu().numpy().astype(np.float64)
+    assert got.min() >= 1
+    # two-sample KS
+    grid = np.arange(1, 501)
+    cdf_g = np.searchsorted(np.sort(got), grid, side="right") / got.size
+    cdf_r = np.searchsorted(np.sort(ref), grid, side="right") / ref.size
+    d = np.max(np.abs(cdf_g - cdf_r))
+    crit = 1.95 * math.sqrt((got.size + ref.size) / (got.size * ref.size))
+    assert d < crit, (d, crit)
+    se_mean = math.sqrt(ref.var() / ref.size + got.var() / got.size)
+    assert abs(got.mean() - ref.mean()) < 5 * se_mean, (got.mean(), ref.mean())
+    assert abs(got.std() / ref.std() - 1) < 0.05
