@@ -181,3 +181,33 @@ def test_port_and_c_vs_live_reference_random_policy():
             if d:
                 break
     assert steps > 5000
+
+
+def test_port_episode_length_law_matches_the_references_demo_loop(golden_dir):
+    """The Python port under the SyncVectorEnv-style harness (the CPU baseline of bench.py) reproduces the law of the
+    reference's own demo loop: 4 000 port episodes vs the 20 000 golden ones, two-sample KS at alpha = 0.001."""
+    import math
+    import os
+    from oracle import dr_port
+    ref = np.load(os.path.join(golden_dir, "cartpole_episode_lengths.npz"))["euler"].astype(np.float64)
+    lo = np.array([b[0] for b in port.SEARCH_BOUNDS]); hi = np.array([b[1] for b in port.SEARCH_BOUNDS])
+    rs = np.random.RandomState(5)
+    env = port.TimeLimitPort(port.CartPolePort())
+    env.env.seed(5)
+    got = []
+    for _ in range(4000):
+        env.set_task(*dr_port.sample_task("uniform", lo, hi, rng=rs))
+        env.reset()
+        T = 0
+        while True:
+            _, _, d, _ = env.step(int(rs.randint(2)))
+            T += 1
+            if d:
+                break
+        got.append(T)
+    got = np.array(got, np.float64)
+    grid = np.arange(1, 501)
+    d = np.max(np.abs(np.searchsorted(np.sort(got), grid, side="right") / got.size
+                      - np.searchsorted(np.sort(ref), grid, side="right") / ref.size))
+    assert d < 1.95 * math.sqrt((got.size + ref.size) / (got.size * ref.size)), d
+    assert abs(got.mean() - ref.mean()) < 5 * math.sqrt(ref.var() / ref.size + got.var() / got.size)
