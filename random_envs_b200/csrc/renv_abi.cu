@@ -120,7 +120,8 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
     c.dr_type = cfg->dr_type;
     c.dim = cfg->dim;
     for (int k = 0; k < 32; ++k) { c.a[k] = cfg->a[k]; c.b[k] = cfg->b[k]; c.lb[k] = cfg->lb[k]; }
-    const int kTile = tile_samples<T>(cfg->dim);
+    const int items = sampler_items<T>(n, cfg->dim);
+    const int kTile = tile_samples<T>(cfg->dim, items);
     const int64_t blocks = (n + kTile - 1) / kTile;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
     // store width follows the row alignment: whole 128-bit blocks, float pairs (e.g. the 30-dim humanoid), scalars
@@ -128,7 +129,7 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
     const int store = cfg->dim % P == 0 ? 0 : (sizeof(T) == 4 && cfg->dim % 2 == 0 ? 1 : 2);
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define RENV_LAUNCH_SAMPLER(TYPE, STORE) \
-    dr_sample_kernel<T, TYPE, STORE><<<(unsigned)blocks, kSampleThreads, 0, st>>>(out, n, c, seed, sample_id0, call, violations)
+    dr_sample_kernel<T, TYPE, STORE><<<(unsigned)blocks, kSampleThreads, 0, st>>>(out, n, c, seed, sample_id0, call, violations, items)
 #define RENV_LAUNCH_SAMPLER_TYPE(TYPE) \
     do { if (store == 0) RENV_LAUNCH_SAMPLER(TYPE, 0); else if (store == 1) RENV_LAUNCH_SAMPLER(TYPE, 1); \
          else RENV_LAUNCH_SAMPLER(TYPE, 2); } while (0)
