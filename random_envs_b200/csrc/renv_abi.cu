@@ -116,10 +116,22 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
             out, n, g, seed, sample_id0, call);
         return launch_status();
     }
-    DrCfgFull c;
+    // host-side image of renv_dr.cuh load_dim_block: same conversions, same order, done once per launch
+    DrCfgPrepared<T> c;
     c.dr_type = cfg->dr_type;
     c.dim = cfg->dim;
-    for (int k = 0; k < 32; ++k) { c.a[k] = cfg->a[k]; c.b[k] = cfg->b[k]; c.lb[k] = cfg->lb[k]; }
+    for (int k = 0; k < 32; ++k) {
+        const bool ok = k < cfg->dim;
+        const T a = ok ? (T)cfg->a[k] : T(0), b = ok ? (T)cfg->b[k] : T(0);
+        c.a[k] = a;
+        if (cfg->dr_type == RENV_DR_UNIFORM) {
+            const T width = b - a;                                          // rounded once, as numpy's `high - low`
+            c.b[k] = sizeof(T) == 4 ? (T)(width * (T)(1.0 / 16777216.0)) : (T)width;   // fp32: 2^-24 folded in (exact)
+        } else {
+            c.b[k] = b;
+        }
+        c.floor[k] = !ok ? T(0) : cfg->dr_type == RENV_DR_TRUNCNORM ? (T)cfg->lb[k] : (T)0.1;
+    }
     const int items = sampler_items<T>(n, cfg->dim);
     const int kTile = tile_samples<T>(cfg->dim, items);
     const int64_t blocks = (n + kTile - 1) / kTile;

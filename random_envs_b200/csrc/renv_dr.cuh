@@ -146,6 +146,29 @@ template <typename T, typename Cfg> __device__ __forceinline__ DimBlock<T> load_
     return blk;
 }
 
+// The same parameters already converted on the host (dr_sample launcher): a thread's set-up is 12 constant-bank loads
+// instead of 12 loads + 12 F2F.F32.F64 conversions + the uniform pre-scaling.
+template <typename T> struct DrCfgPrepared {
+    int dr_type, dim;
+    T a[32], b[32], floor[32];       // b: (hi - lo) [* 2^-24 for fp32] (uniform) or std; floor: lb (truncnorm) / 0.1 (gaussian)
+};
+template <typename T> __device__ __forceinline__ DimBlock<T> load_dim_block(const DrCfgPrepared<T> &cfg, int j)
+{
+    constexpr int P = Pack<T>::kPerBlock;
+    DimBlock<T> blk;
+    blk.valid = 0;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        const int d = j * P + k;
+        const bool ok = d < cfg.dim;
+        blk.a[k] = ok ? cfg.a[d] : T(0);
+        blk.b[k] = ok ? cfg.b[d] : T(0);
+        blk.floor[k] = ok ? cfg.floor[d] : T(0);
+        if (ok) blk.valid |= 1u << k;
+    }
+    return blk;
+}
+
 // One standard draw per dim of the block for attempt `t`: truncnorm -> TN(-2,2) by inverse CDF, gaussian -> N(0,1).
 template <typename T>
 __device__ __forceinline__ void standard_draws(bool tn, uint64_t seed, uint64_t id, uint64_t tick, uint32_t purpose,

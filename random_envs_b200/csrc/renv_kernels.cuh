@@ -541,7 +541,6 @@ template <typename T> __host__ __device__ inline int tile_samples(int dim, int i
     return (kSampleThreads * items) >> sampler_log2pad<T>(dim);
 }
 
-struct DrCfgFull { int dr_type; int dim; double a[32]; double b[32]; double lb[32]; };
 
 // Work item = (sample, dim block of 4 floats / 2 doubles = one Philox call).  Thread t owns dim block
 // j = t % jpad (jpad = blocks per sample rounded up to a power of two) for the whole kernel, so its distribution
@@ -584,7 +583,7 @@ template <> __device__ __forceinline__ void store_block<double, 1>(double *row, 
 }
 
 template <typename T, int kDrType, int kStore>
-__global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict__ out, int64_t n, const DrCfgFull cfg,
+__global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict__ out, int64_t n, const DrCfgPrepared<T> cfg,
                                                                    uint64_t seed, uint64_t sample_id0, uint32_t call,
                                                                    unsigned long long *violations, int items)
 {
@@ -599,7 +598,7 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
     const int64_t first = (int64_t)blockIdx.x * kTile;
     const int samples = (int)min((int64_t)kTile, n - first);
     if (j >= blocks_per_sample) return;
-    const DimBlock<T> blk = load_dim_block<T>(cfg, j);
+    const DimBlock<T> blk = load_dim_block(cfg, j);
     unsigned viol = 0;
     T *const tile = out + (first + lane_sample) * dim + j * P;      // 64-bit once; 32-bit offsets inside the tile
     const int row_step = samples_per_pass * dim;
