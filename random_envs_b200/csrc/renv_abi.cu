@@ -18,18 +18,35 @@ namespace {
 
 inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-int to_cfg4(const renv_dr_cfg *dr, DrCfg4 *out)
+// Host-side conversion of the 4-dim DR configuration to the kernels' element type: the same casts, the same
+// rounded-once `hi - lo` and the exact 2^-24 folding the device code used to do per reset.
+template <typename T> int to_cfg4(const renv_dr_cfg *dr, DrCfg4<T> *out)
 {
     out->dr_type = kDrNone;
     out->dim = 4;
-    for (int k = 0; k < 4; ++k) { out->a[k] = 0.0; out->b[k] = 0.0; out->lb[k] = 0.0; }
-    for (int k = 0; k < 16; ++k) out->factor[k] = 0.0;
+    for (int k = 0; k < 4; ++k) { out->a[k] = T(0); out->b[k] = T(0); out->floor[k] = T(0); }
+    for (int k = 0; k < 16; ++k) out->factor[k] = T(0);
     if (dr == nullptr || dr->dr_type == RENV_DR_NONE) return RENV_OK;
     if (dr->dr_type < RENV_DR_NONE || dr->dr_type > RENV_DR_FULLGAUSSIAN) return RENV_E_DRTYPE;
     if (dr->dim != 4) return RENV_E_DIM;
     out->dr_type = dr->dr_type;
-    for (int k = 0; k < 4; ++k) { out->a[k] = dr->a[k]; out->b[k] = dr->b[k]; out->lb[k] = dr->lb[k]; }
-    for (int k = 0; k < 16; ++k) out->factor[k] = dr->dr_type == RENV_DR_FULLGAUSSIAN ? dr->factor[k] : 0.0;
+    for (int k = 0; k < 4; ++k) {
+        const T a = (T)dr->a[k], b = (T)dr->b[k];
+        out->a[k] = a;
+        if (dr->dr_type == RENV_DR_UNIFORM) {
+            const T width = b - a;
+            out->b[k] = sizeof(T) == 4 ? (T)(width * (T)(1.0 / 16777216.0)) : width;
+            out->floor[k] = T(0);
+        } else if (dr->dr_type == RENV_DR_FULLGAUSSIAN) {
+            out->b[k] = b;                       // search-bound lo
+            out->floor[k] = (T)dr->lb[k];        // search-bound hi
+        } else {
+            out->b[k] = b;
+            out->floor[k] = dr->dr_type == RENV_DR_TRUNCNORM ? (T)dr->lb[k] : (T)0.1;
+        }
+    }
+    if (dr->dr_type == RENV_DR_FULLGAUSSIAN)
+        for (int k = 0; k < 16; ++k) out->factor[k] = (T)dr->factor[k];
     return RENV_OK;
 }
 
@@ -162,7 +179,7 @@ int cartpole_reset(const renv_cartpole_env *env, const renv_obs_noise *noise, co
     if (rc) return rc;
     rc = attach_noise<T>(noise, &a.env);
     if (rc) return rc;
-    rc = to_cfg4(dr, &a.dr);
+    rc = to_cfg4<T>(dr, &a.dr);
     if (rc) return rc;
     a.mask = mask;
     a.tick = tick;
@@ -209,7 +226,7 @@ int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, con
     if (!aligned(action, 4) || !aligned(reward, 16) || !aligned(done, 4) || (truncated && !aligned(truncated, 4)))
         return RENV_E_ALIGN;
     if (integrator != RENV_EULER && integrator != RENV_SEMI_IMPLICIT) return RENV_E_INTEGRATOR;
-    rc = to_cfg4(auto_reset ? dr : nullptr, &a.dr);
+    rc = to_cfg4<T>(auto_reset ? dr : nullptr, &a.dr);
     if (rc) return rc;
     a.action = action; a.reward = reward; a.done = done; a.truncated = truncated;
     a.euler = integrator == RENV_EULER;
@@ -289,7 +306,7 @@ int cartpole_rollout(const renv_cartpole_env *env, const renv_obs_noise *noise, 
     if (!aligned(stats, 8)) return RENV_E_ALIGN;
     if (K <= 0 || K > (1 << 30)) return RENV_E_SIZE;      // per-thread step counters are 32-bit
     if (integrator != RENV_EULER && integrator != RENV_SEMI_IMPLICIT) return RENV_E_INTEGRATOR;
-    rc = to_cfg4(dr, &a.dr);
+    rc = to_cfg4<T>(dr, &a.dr);
     if (rc) return rc;
     a.policy = w ? Policy<T>{ (T)w[0], (T)w[1], (T)w[2], (T)w[3], (T)b } : Policy<T>{ T(0), T(0), T(0), T(0), T(0) };
     a.K = K;

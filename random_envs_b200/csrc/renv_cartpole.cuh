@@ -261,7 +261,7 @@ __device__ __forceinline__ void add_obs_noise(const State<double> &s, double std
 // Deliberately NOT inlined: it is the rarest branch of the (already cold) reset path and inlining it costs the
 // fused rollout kernel 40 registers.  `cfg` points into the kernel's __grid_constant__ parameter block.
 template <typename T>
-__device__ __noinline__ void fullgaussian_xi(const DrCfg4 *cfg, uint64_t seed, uint64_t id, uint64_t tick, T *v)
+__device__ __noinline__ void fullgaussian_xi(const DrCfg4<T> *cfg, uint64_t seed, uint64_t id, uint64_t tick, T *v)
 {
     constexpr int P = Pack<T>::kPerBlock;
     T z[4];
@@ -269,15 +269,15 @@ __device__ __noinline__ void fullgaussian_xi(const DrCfg4 *cfg, uint64_t seed, u
     for (int j = 0; j < 4 / P; ++j) Num<T>::normals(draw_block(seed, id, tick, kXi, (uint32_t)j), z + j * P);
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-        T x = (T)cfg->a[d];
+        T x = cfg->a[d];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) x = Num<T>::affine((T)cfg->factor[d * 4 + k], z[k], x);
-        v[d] = denormalize(x, (T)cfg->b[d], (T)cfg->lb[d]);
+        for (int k = 0; k < 4; ++k) x = Num<T>::affine(cfg->factor[d * 4 + k], z[k], x);
+        v[d] = denormalize(x, cfg->b[d], cfg->floor[d]);
     }
 }
 
 template <typename T>
-__device__ __forceinline__ unsigned sample_xi(Xi<T> &p, const DrCfg4 &cfg, uint64_t seed, uint64_t id, uint64_t tick)
+__device__ __forceinline__ unsigned sample_xi(Xi<T> &p, const DrCfg4<T> &cfg, uint64_t seed, uint64_t id, uint64_t tick)
 {
     constexpr int P = Pack<T>::kPerBlock;
     T v[4] = { p.gravity, p.cart_mass, p.pole_mass, p.pole_length };

@@ -25,14 +25,17 @@ constexpr double kGaussianFloor = 0.1;                   // random_env.py:181 (h
 
 enum DrType : int { kDrNone = 0, kDrUniform = 1, kDrTruncnorm = 2, kDrGaussian = 3, kDrFullGaussian = 4 };
 
-// Compact 4-dim image of renv_dr_cfg for the cart-pole kernels (passed by value as a kernel parameter).
-// fullgaussian (random_env.py:192-198): a = mean in the normalised [0,4] space, b / lb = search-bound lo / hi,
-// factor = any F with F F^T = cov (row-major 4x4).
-struct DrCfg4 {
+// Compact 4-dim image of renv_dr_cfg for the cart-pole kernels (passed by value as a kernel parameter), already
+// converted to the element type on the host (renv_abi.cu to_cfg4) so that a reset pays no F2F conversions:
+//   uniform:            a = lo, b = hi - lo (fp32: times 2^-24, see Pack<float>::uniform_affine)
+//   truncnorm/gaussian: a = mean, b = std, floor = lower bound / 0.1
+//   fullgaussian (random_env.py:192-198): a = mean in the normalised [0,4] space, b / floor = search-bound lo / hi,
+//                       factor = any F with F F^T = cov (row-major 4x4).
+template <typename T> struct DrCfg4 {
     int dr_type;
     int dim;
-    double a[4], b[4], lb[4];
-    double factor[16];
+    T a[4], b[4], floor[4];
+    T factor[16];
 };
 
 template <typename T> struct Num;
@@ -128,30 +131,23 @@ template <typename T> struct DimBlock {
     unsigned valid;              // bit k set <=> dim j*P + k exists
 };
 
-template <typename T, typename Cfg> __device__ __forceinline__ DimBlock<T> load_dim_block(const Cfg &cfg, int j)
-{
-    constexpr int P = Pack<T>::kPerBlock;
-    DimBlock<T> blk;
-    blk.valid = 0;
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-        const int d = j * P + k;
-        const bool ok = d < cfg.dim;
-        blk.a[k] = ok ? (T)cfg.a[d] : T(0);
-        // scale: hi - lo for uniform (rounded once, as numpy's `high - low`; fp32: times 2^-24, see uniform_affine), std otherwise
-        blk.b[k] = ok ? (cfg.dr_type == kDrUniform ? Pack<T>::uniform_scale(Num<T>::sub((T)cfg.b[d], (T)cfg.a[d])) : (T)cfg.b[d]) : T(0);
-        blk.floor[k] = ok ? (cfg.dr_type == kDrTruncnorm ? (T)cfg.lb[d] : (T)kGaussianFloor) : T(0);
-        if (ok) blk.valid |= 1u << k;
-    }
-    return blk;
-}
-
 // The same parameters already converted on the host (dr_sample launcher): a thread's set-up is 12 constant-bank loads
 // instead of 12 loads + 12 F2F.F32.F64 conversions + the uniform pre-scaling.
 template <typename T> struct DrCfgPrepared {
     int dr_type, dim;
     T a[32], b[32], floor[32];       // b: (hi - lo) [* 2^-24 for fp32] (uniform) or std; floor: lb (truncnorm) / 0.1 (gaussian)
 };
+template <typename T> __device__ __forceinline__ DimBlock<T> load_dim_block(const DrCfg4<T> &cfg, int j)
+{
+    constexpr int P = Pack<T>::kPerBlock;
+    DimBlock<T> blk;
+    blk.valid = (1u << P) - 1u;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        blk.a[k] = cfg.a[j * P + k]; blk.b[k] = cfg.b[j * P + k]; blk.floor[k] = cfg.floor[j * P + k];
+    }
+    return blk;
+}
 template <typename T> __device__ __forceinline__ DimBlock<T> load_dim_block(const DrCfgPrepared<T> &cfg, int j)
 {
     constexpr int P = Pack<T>::kPerBlock;
@@ -252,7 +248,7 @@ template <typename T, typename Cfg>
 __device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t seed, uint64_t id, uint64_t tick,
                                                      uint32_t purpose, int j, T *out)
 {
-    return sample_dim_block<T>(cfg.dr_type, load_dim_block<T>(cfg, j), seed, id, tick, purpose, j, out);
+    return sample_dim_block<T>(cfg.dr_type, load_dim_block(cfg, j), seed, id, tick, purpose, j, out);
 }
 
 }  // namespace renv

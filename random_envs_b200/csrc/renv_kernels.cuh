@@ -71,7 +71,7 @@ template <typename T> struct EnvPtrs {
 
 // RandomCartPoleEnv.reset (+ set_random_task) of env i at clock `tick`; scalar stores.
 template <typename T>
-__device__ __forceinline__ unsigned reset_env(const EnvPtrs<T> &env, const DrCfg4 &dr, int64_t i, uint64_t tick)
+__device__ __forceinline__ unsigned reset_env(const EnvPtrs<T> &env, const DrCfg4<T> &dr, int64_t i, uint64_t tick)
 {
     const int64_t ld = env.ld;
     const uint64_t id = env.env_id0 + (uint64_t)i;
@@ -102,7 +102,7 @@ template <typename T> struct StepArgs {
     const uint8_t *action; T *reward; uint8_t *done; uint8_t *truncated;
     int euler, max_steps;
     uint64_t tick;
-    DrCfg4 dr;
+    DrCfg4<T> dr;
     unsigned long long *violations;
 };
 
@@ -252,7 +252,7 @@ template <typename T> struct ResetArgs {
     EnvPtrs<T> env;
     const uint8_t *mask;
     uint64_t tick;
-    DrCfg4 dr;
+    DrCfg4<T> dr;
     unsigned long long *violations;
 };
 
@@ -343,7 +343,7 @@ template <typename T> struct RolloutArgs {
     Policy<T> policy;
     int K, euler, max_steps;
     uint64_t tick;
-    DrCfg4 dr;
+    DrCfg4<T> dr;
     double *stats;
     unsigned long long *violations;
 };
