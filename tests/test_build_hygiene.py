@@ -1,0 +1,80 @@
+"""T6 build hygiene, no GPU needed: the built library is sm_100a code with the instruction forms the
+design relies on -- 128-bit global accesses in the step kernel, packed FFMA2 in the fp32 rollout, FP64 FMAs in the fp64
+one, programmatic-dependent-launch instructions, no register spills in the rollout kernels."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "profiles"))
+import sass_stats  # noqa: E402
+
+from random_envs_b200 import build as lib_build  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def sass():
+    lib_build.build()
+    return sass_stats.functions(lib_build.LIB_PATH)
+
+
+def _ops(rows):
+    return [op for _, op, _ in rows]
+
+
+def _one(sass, *needles):
+    hits = [name for name in sass if all(n in name for n in needles)]
+    assert len(hits) == 1, (needles, hits)
+    return sass[hits[0]]
+
+
+def test_library_targets_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", lib_build.LIB_PATH], stdout=subprocess.PIPE, text=True, check=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_step_kernel_uses_128_bit_accesses_and_programmatic_dependent_launch(sass):
+    ops = _ops(_one(sass, "cartpole_step_kernelIfLb1ELb0"))        # <float, auto_reset, not noisy>: the hot kernel
+    assert sum(o.startswith("LDG.E.128") for o in ops) >= 9        # 4 state rows + 4 xi rows + elapsed
+    assert sum(o.startswith("STG.E.128") for o in ops) >= 6        # 4 state rows + elapsed + reward
+    assert "ACQBULK" in ops and "PREEXIT" in ops                   # griddepcontrol.wait / launch_dependents
+    ops64 = _ops(_one(sass, "cartpole_step_kernelIdLb1ELb0"))
+    assert sum(o.startswith("LDG.E.128") for o in ops64) >= 10 and any(o.startswith("DFMA") for o in ops64)
+
+
+def test_fp32_rollout_runs_on_the_packed_fp32_pipe_and_fp64_rollout_on_dfma(sass):
+    pair = _ops(_one(sass, "cartpole_rollout_pair_kernelILb1"))
+    assert sum(o.startswith("FFMA2") for o in pair) >= 100 and sum(o.startswith("FMUL2") for o in pair) >= 50
+    f64 = _ops(_one(sass, "cartpole_rollout_kernelIdLb1ELb0ELb0"))
+    assert sum(o.startswith("DFMA") for o in f64) > 500 and not any(o.startswith("FFMA2") for o in f64)
+
+
+def test_uniform_sampler_loop_is_philox_plus_conversion_only(sass):
+    rows = _one(sass, "dr_sample_kernelIfLi1ELi0")                  # <float, uniform, 128-bit stores>
+    ops = _ops(rows)
+    assert sum(o.startswith("IMAD.WIDE.U32") for o in ops) >= 19   # Philox4x32-10: 2 per round
+    assert not any(o.startswith("F2F") for o in ops)               # parameters arrive converted (host side)
+    assert any(o.startswith("STG.E.128") for o in ops)
+
+
+def test_no_register_spills_in_the_rollout_kernels():
+    log = open(os.path.join(ROOT, "random_envs_b200", "librenv_b200.ptxas.log")).read()
+    blocks = re.split(r"ptxas info\s+: Compiling entry function '", log)[1:]
+    seen = 0
+    for b in blocks:
+        name = b.split("'")[0]
+        if "rollout" in name:
+            m = re.search(r"(\d+) bytes spill stores, (\d+) bytes spill loads", b)
+            main = "rollout_pair" in name or name.endswith("ELb0ELb0EEEvNS_11RolloutArgsIT_EE")   # fp32 pair / plain fp64
+            if main:
+                assert m and m.group(1) == "0" and m.group(2) == "0", (name, m and m.groups())
+            else:                       # noisy / random-policy variants: a few registers over the 3-CTA cap are tolerated
+                assert m and int(m.group(1)) <= 128, (name, m and m.groups())
+            regs = int(re.search(r"Used (\d+) registers", b).group(1))
+            assert regs <= 80, (name, regs)                          # 3 CTAs of 256 threads per SM
+            seen += 1
+    assert seen >= 8
