@@ -106,14 +106,17 @@ template <typename T> struct StepArgs {
     unsigned long long *violations;
 };
 
-constexpr int kStepThreads = 256;
+#ifndef RENV_STEP_THREADS
+#define RENV_STEP_THREADS 256
+#endif
+constexpr int kStepThreads = RENV_STEP_THREADS;
 
 // kAutoReset = true is the hot kernel.  Finished envs are NOT reset by the thread that owns them (that would
 // run the ~250-instruction Philox/sampling path once per warp per finished lane with ~1 active lane): their
 // CTA-local indices are appended to a shared-memory list and, after one __syncthreads, the first `count`
 // threads of the CTA each reset one env at full lane utilisation, overwriting the owner's stores.
 template <typename T, bool kAutoReset, bool kNoisy = false>
-__global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3)) cartpole_step_kernel(const __grid_constant__ StepArgs<T> a)
+__global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 / kStepThreads) cartpole_step_kernel(const __grid_constant__ StepArgs<T> a)
 {
     using VT = VecTraits<T>;
     constexpr int V = VT::V;
