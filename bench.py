@@ -53,7 +53,9 @@ def workload_config(args, world):
             "l2_policy": "inputs larger than L2: %d batches x %.0f MB round-robin per GPU"
                          % (args.batches, args.envs * BYTES_PER_STEP[args.dtype] / 1e6),
             "policy": "random (Bernoulli(1/2) uint8 actions, Philox, pre-generated on device)",
-            "max_episode_steps": 500, "integrator": "euler", "parallelism": "envs sharded by index, dp%d" % world}
+            "max_episode_steps": 500, "integrator": "euler", "parallelism": "envs sharded by index, dp%d" % world,
+            "outputs": "state (= obs), reward, done, elapsed: the 62 B/env-step of SURVEY 8d; the optional "
+                       "TimeLimit.truncated flags (+1 B) and per-env episode counters are off"}
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
