@@ -82,6 +82,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         self.polemass_length = 0.05     # frozen, as in the reference (:79 vs :157-166)
         self._buffers = None
         self._cfg_cache = None
+        self._cfg_key = None
         self._tick = 0                  # step clock: Philox episode key; +1 per reset/step, +K per rollout
 
     # ---- xi tables (random_cartpole.py:123-147) ----------------------------------------------------
@@ -162,8 +163,13 @@ class RandomCartPoleVecEnv(RandomEnv):
         """DR config used on reset: only when dr_training is on and a distribution is loaded."""
         if not self.dr_training or self.sampling is None:
             return None
-        if self._cfg_cache is None:
-            self._cfg_cache = self.dr_config()
+        # the reference reads min/max/mean/stdev_task at every draw, so in-place edits of those arrays must take
+        # effect: the cached struct is keyed by their bytes (4 x 32 B, ~1 us)
+        key = (self.sampling, self.min_task.tobytes(), self.max_task.tobytes(), self.mean_task.tobytes(),
+               self.stdev_task.tobytes(),
+               np.asarray(self.cov_task).tobytes() if self.sampling == "fullgaussian" else None)
+        if self._cfg_cache is None or self._cfg_key != key:
+            self._cfg_cache, self._cfg_key = self.dr_config(), key
         return ctypes.byref(self._cfg_cache)
 
     # ---- gym-style API ------------------------------------------------------------------------------

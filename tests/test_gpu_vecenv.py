@@ -347,3 +347,18 @@ def test_random_policy_rollout_equals_step_with_sample_actions(dtype, n, K, limi
     assert st["episodes"] == ends
     if n >= 1000 and limit == 500:
         assert 15 < st["mean_return"] < 40                    # random policy over the search bounds: ~27 steps
+
+
+def test_in_place_edits_of_the_distribution_arrays_take_effect():
+    """The reference reads min_task / max_task at every draw (random_env.py:151): editing them in place between steps
+    changes what the next reset samples, without calling set_dr_distribution again."""
+    env = random_envs.RandomCartPoleVecEnv(4096, dtype="float64", seed=3, max_episode_steps=1)   # every step resets
+    env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True)
+    env.reset()
+    env.step(env.sample_actions())
+    g = _np(env.get_task())[:, 0]
+    assert g.min() >= 2.0 and g.max() <= 20.0 and g.max() > 15.0
+    env.min_task[0], env.max_task[0] = 30.0, 31.0
+    env.step(env.sample_actions())
+    g = _np(env.get_task())[:, 0]
+    assert g.min() >= 30.0 and g.max() <= 31.0
