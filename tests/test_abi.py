@@ -75,3 +75,30 @@ def test_strerror_and_argument_validation_without_a_gpu():
 def test_unknown_dr_type_raises_reference_message():
     with pytest.raises(Exception, match="Unknown dr_type:beta"):
         _lib.make_dr_cfg("beta", [0.0], [1.0])
+
+
+def test_noisy_and_rollout_argument_validation_without_a_gpu():
+    lib = _lib.load()
+    env = _lib.CartpoleEnv()
+    env.state = env.xi = env.elapsed = env.episode = env.beyond = 4096
+    env.n, env.ld = 10, 12
+    w = (ctypes.c_double * 4)(0, 0, 1, 0)
+    noise = _lib.ObsNoise()
+    assert lib.renv_cartpole_step_noisy_f32(ctypes.byref(env), None, 4096, 4096, 4096, None, 0, 500, 1, 0, None, None, None) == -1
+    assert lib.renv_cartpole_reset_noisy_f64(ctypes.byref(env), ctypes.byref(noise), None, 0, None, None, None) == -1   # obs NULL
+    noise.obs, noise.std = 4100, 0.1
+    assert lib.renv_cartpole_reset_noisy_f32(ctypes.byref(env), ctypes.byref(noise), None, 0, None, None, None) == -2   # obs alignment
+    noise.obs, noise.std = 4096, -1.0
+    assert lib.renv_cartpole_step_noisy_f32(ctypes.byref(env), ctypes.byref(noise), 4096, 4096, 4096, None, 0, 500, 1, 0, None,
+                                            None, None) == -7                                                           # std < 0
+    noise.std = float("nan")
+    assert lib.renv_cartpole_rollout_noisy_f32(ctypes.byref(env), ctypes.byref(noise), w, 0.0, 5, 0, 500, 0, None, 4096, None,
+                                               None) == -7
+    noise.std = 0.1
+    assert lib.renv_cartpole_rollout_noisy_f64(ctypes.byref(env), ctypes.byref(noise), None, 0.0, 5, 0, 500, 0, None, 4096, None,
+                                               None) == -7                      # the random policy ignores observations
+    assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, (1 << 30) + 1, 0, 500, 0, None, 4096, None, None) == -3
+    assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 5, 0, 500, 0, None, None, None, None) == -1            # stats NULL
+    assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 5, 0, 500, 0, None, 4100, None, None) == -2            # stats alignment
+    cfg = _lib.make_dr_cfg("uniform", [0.0] * 5, [1.0] * 5)
+    assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 5, 0, 500, 0, ctypes.byref(cfg), 4096, None, None) == -4   # dim != 4
