@@ -101,6 +101,19 @@ class RandomEnv(Env):
             self.mean_task[:] = distr["mean"]
             self.cov_task = np.copy(distr["cov"])
 
+    # the reference's private per-type setters (random_env.py:102-127), kept for code that calls them directly
+    def _set_udr_distribution(self, bounds):
+        self.set_dr_distribution("uniform", bounds)
+
+    def _set_truncnorm_distribution(self, bounds):
+        self.set_dr_distribution("truncnorm", bounds)
+
+    def _set_gaussian_distribution(self, bounds):
+        self.set_dr_distribution("gaussian", bounds)
+
+    def _set_fullgaussian_distribution(self, mean, cov):
+        self.set_dr_distribution("fullgaussian", {"mean": mean, "cov": cov})
+
     @staticmethod
     def _fill_interleaved(distr, first, second):
         # range(len//2): a short list sets a prefix, a long one raises IndexError like the reference
