@@ -123,14 +123,20 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
     if (cfg->dr_type == RENV_DR_FULLGAUSSIAN) {
         FullGaussCfg<T> g;
         g.dim = cfg->dim;
-        for (int k = 0; k < 32; ++k) { g.mean[k] = (T)cfg->a[k]; g.lo[k] = (T)cfg->b[k]; g.hi[k] = (T)cfg->lb[k]; }
-        for (int k = 0; k < cfg->dim * cfg->dim; ++k) g.factor[k] = (T)cfg->factor[k];
-        for (int k = cfg->dim * cfg->dim; k < 32 * 32; ++k) g.factor[k] = T(0);
-        constexpr int kTileG = fullgauss_tile<T>();
-        const int64_t gblocks = (n + kTileG - 1) / kTileG;
+        for (int k = 0; k < 32; ++k) {
+            const bool ok = k < cfg->dim;
+            g.mean[k] = ok ? (T)cfg->a[k] : T(0); g.lo[k] = ok ? (T)cfg->b[k] : T(0); g.hi[k] = ok ? (T)cfg->lb[k] : T(0);
+        }
+        for (int k = 0; k < 32; ++k)                 // transposed, zero-padded: ft[k][d] = F[d][k]
+            for (int d = 0; d < 32; ++d)
+                g.ft[k * 32 + d] = (k < cfg->dim && d < cfg->dim) ? (T)cfg->factor[d * cfg->dim + k] : T(0);
+        const int64_t gblocks = (n + kFullGaussThreads - 1) / kFullGaussThreads;
         if (gblocks > 0x7fffffffLL) return RENV_E_SIZE;
-        dr_sample_fullgaussian_kernel<T><<<(unsigned)gblocks, kSampleThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            out, n, g, seed, sample_id0, call);
+        const cudaStream_t gst = static_cast<cudaStream_t>(stream);
+        if (cfg->dim <= 4) dr_sample_fullgaussian_kernel<T, 4><<<(unsigned)gblocks, kFullGaussThreads, 0, gst>>>(out, n, g, seed, sample_id0, call);
+        else if (cfg->dim <= 8) dr_sample_fullgaussian_kernel<T, 8><<<(unsigned)gblocks, kFullGaussThreads, 0, gst>>>(out, n, g, seed, sample_id0, call);
+        else if (cfg->dim <= 16) dr_sample_fullgaussian_kernel<T, 16><<<(unsigned)gblocks, kFullGaussThreads, 0, gst>>>(out, n, g, seed, sample_id0, call);
+        else dr_sample_fullgaussian_kernel<T, 32><<<(unsigned)gblocks, kFullGaussThreads, 0, gst>>>(out, n, g, seed, sample_id0, call);
         return launch_status();
     }
     // host-side image of renv_dr.cuh load_dim_block: same conversions, same order, done once per launch

@@ -621,56 +621,72 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
 // ------------------------------------------------------------------------------------------------
 // sample_tasks(n) for dr_type 'fullgaussian' (random_env.py:192-198): x = mean + F z, clip [0,4], denormalise
 // ------------------------------------------------------------------------------------------------
+// A batched dim x dim mat-vec: 2 dim^2 FLOPs per sample against dim * sizeof(T) output bytes -- FMA-bound for the
+// 30-dim humanoid.  One thread = one sample with all (padded) 32 outputs as register accumulators; z is produced
+// one Philox block at a time and never stored.  The factor arrives TRANSPOSED and zero-padded to 32 x 32 in the
+// kernel parameter block (constant bank), and the k loop is fully unrolled, so every coefficient is an immediate
+// constant-bank operand of its FMA: no load instruction at all in the inner product.
+//   v1: one output element per thread, two LDS per FMA            11.6 ms for 2^24 x 30 fp32
+//   v2: register accumulators, factor broadcast from shared memory   2.2 ms (LSU-bound: an LDS.128 broadcast still
+//       costs 4 wavefronts, 256 of them per sample)
+//   v3: factor as constant-bank operands                             see DESIGN.md
+// Summation order (k ascending, FMA) is the same in all three, so the values never changed.  Rows are staged per
+// warp in shared memory and written as 128-bit chunks.
 template <typename T> struct FullGaussCfg {
     int dim;
     T mean[32], lo[32], hi[32];
-    T factor[32 * 32];           // row-major F, F F^T = cov  (4.4 KB fp32 / 8.8 KB fp64: a large kernel parameter)
+    T ft[32 * 32];               // ft[k * 32 + d] = F[d][k] (F F^T = cov), zero beyond dim: 4 KB fp32 / 8 KB fp64
 };
-template <typename T> __host__ __device__ constexpr int fullgauss_tile() { return 512 / (int)sizeof(T); }   // 128 / 64 rows
+#ifndef RENV_FULLGAUSS_CTAS
+#define RENV_FULLGAUSS_CTAS 4
+#endif
+constexpr int kFullGaussThreads = 128;
 
-template <typename T>
-__global__ void __launch_bounds__(kSampleThreads) dr_sample_fullgaussian_kernel(T *__restrict__ out, int64_t n,
-                                                                                const __grid_constant__ FullGaussCfg<T> cfg,
-                                                                                uint64_t seed, uint64_t sample_id0,
-                                                                                uint32_t call)
+// D = dim rounded up to {4, 8, 16, 32}: accumulators and unrolled loops are sized for it (a 4-dim cart-pole sample is
+// 16 FMAs, not 1024).
+template <typename T, int D>
+__global__ void __launch_bounds__(kFullGaussThreads, RENV_FULLGAUSS_CTAS)
+dr_sample_fullgaussian_kernel(T *__restrict__ out, int64_t n, const __grid_constant__ FullGaussCfg<T> cfg, uint64_t seed,
+                              uint64_t sample_id0, uint32_t call)
 {
     constexpr int P = Pack<T>::kPerBlock;
-    constexpr int kTile = fullgauss_tile<T>();
-    __shared__ __align__(16) T zt[kTile * 32];
-    __shared__ __align__(16) T xt[kTile * 32];
-    __shared__ T fs[32 * 32];    // the factor, staged once: per-lane rows would serialise on the constant bank
+    constexpr int W = 16 / (int)sizeof(T);                      // elements per 128-bit access
+    __shared__ __align__(16) T stage[kFullGaussThreads * D];    // per warp: 32 rows of `dim` values, contiguous
     const int dim = cfg.dim;
-    for (int q = threadIdx.x; q < dim * dim; q += blockDim.x) fs[q] = cfg.factor[q];
-    const int blocks_per_sample = (dim + P - 1) / P;
-    const int64_t first = (int64_t)blockIdx.x * kTile;
-    const int samples = (int)min((int64_t)kTile, n - first);
-    // phase 1: standard normals, one Philox block per (sample, dim block)
-    for (int it = threadIdx.x; it < samples * blocks_per_sample; it += blockDim.x) {
-        const int sidx = it / blocks_per_sample, j = it - sidx * blocks_per_sample;
-        T z[P];
-        Num<T>::normals(draw_block(seed, sample_id0 + (uint64_t)(first + sidx), call, kTasks, (uint32_t)j), z);
+    const int64_t i = (int64_t)blockIdx.x * kFullGaussThreads + threadIdx.x;
+    const uint64_t id = sample_id0 + (uint64_t)i;
+    T x[D];
 #pragma unroll
-        for (int k = 0; k < P; ++k)
-            if (j * P + k < dim) zt[sidx * dim + j * P + k] = z[k];
+    for (int d = 0; d < D; ++d) x[d] = cfg.mean[d];             // zero beyond dim (host)
+    if (i < n) {
+#pragma unroll
+        for (int j = 0; j < D / P; ++j) {
+            if (j * P < dim) {                                  // uniform branch; rows k >= dim of ft are zero anyway
+                T z[P];
+                Num<T>::normals(draw_block(seed, id, call, kTasks, (uint32_t)j), z);
+#pragma unroll
+                for (int kk = 0; kk < P; ++kk)
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+                        x[d] = Num<T>::affine(cfg.ft[(j * P + kk) * 32 + d], z[kk], x[d]);
+            }
+        }
     }
-    __syncthreads();
-    // phase 2: one output element per thread-iteration: dim FMAs against the factor row
-    for (int e = threadIdx.x; e < samples * dim; e += blockDim.x) {
-        const int sidx = e / dim, d = e - sidx * dim;
-        T x = cfg.mean[d];
-        const T *zr = zt + sidx * dim;
-        const T *fr = fs + d * dim;
-        for (int k = 0; k < dim; ++k) x = Num<T>::affine(fr[k], zr[k], x);
-        xt[e] = denormalize(x, cfg.lo[d], cfg.hi[d]);
-    }
-    __syncthreads();
-    const int total = samples * dim;
-    T *dst = out + first * dim;
-    constexpr int W = 16 / sizeof(T);
+    // clip, denormalise, stage the row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *tile = stage + warp * 32 * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        if (d < dim) tile[lane * dim + d] = denormalize(x[d], cfg.lo[d], cfg.hi[d]);
+    __syncwarp();
+    const int64_t warp_first = (int64_t)blockIdx.x * kFullGaussThreads + warp * 32;
+    const int rows = (int)max((int64_t)0, min((int64_t)32, n - warp_first));
+    const int total = rows * dim;
+    T *dst = out + warp_first * dim;                            // 32 * dim * sizeof(T) is a multiple of 128 bytes
     const int nvec = total / W;
-    for (int q = threadIdx.x; q < nvec; q += blockDim.x)
-        reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(xt)[q];
-    for (int q = nvec * W + threadIdx.x; q < total; q += blockDim.x) dst[q] = xt[q];
+    for (int q = lane; q < nvec; q += 32)
+        reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(tile)[q];
+    for (int q = nvec * W + lane; q < total; q += 32) dst[q] = tile[q];
 }
 
 // ------------------------------------------------------------------------------------------------
