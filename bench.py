@@ -454,11 +454,15 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
     # BASELINE configs[4]: humanoid 30-dim sampler sweep, 2^24 samples per call
     nu = list(renv.HUMANOID_NOMINAL)
     n = 1 << 24
-    for dr_type in ("uniform", "gaussian", "truncnorm"):
+    for dr_type in ("uniform", "gaussian", "truncnorm", "fullgaussian"):
         s = renv.TaskSampler("RandomHumanoid-v0")
         distr = []
         for v in nu:
             distr += [0.5 * v, 1.5 * v] if dr_type == "uniform" else [v, 0.1 * v]
+        if dr_type == "fullgaussian":      # correlated normal in the normalised [0, 4] space (dim x dim mat-vec)
+            import numpy as np
+            a = np.random.RandomState(0).randn(30, 30) * 0.1
+            distr = {"mean": np.full(30, 2.0), "cov": a @ a.T + 0.05 * np.eye(30)}
         s.set_dr_distribution(dr_type, distr)
         buf = torch.empty((n, 30), dtype=torch.float32, device=dev)
         s.sample_tasks_tensor(n, out=buf); torch.cuda.synchronize()
