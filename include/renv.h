@@ -18,6 +18,16 @@
  *     (n, 4) row-major: columns gravity, cart_mass, pole_mass, pole_length (order of
  *     random_envs/random_cartpole.py:104-107,149-155) -- the layout of get_task() / sample_tasks(n), and a reset
  *     rewrites one 32-byte sector instead of four.
+ *   - Errors the reference raises from inside the computation are detected on the device and COUNTED in
+ *     `counters` (device pointer to RENV_NUM_COUNTERS uint64, caller-zeroed, may be NULL; the entry points that can
+ *     only produce the first kind call it `violations`):
+ *       counters[0]  gaussian DR dims whose three draws were all < 0.1 (random_env.py:181-186: the reference raises
+ *                    Exception('Not all samples were above > 0.1 after 2 attempts'); here the dim is set to 0.1),
+ *       counters[1]  step launches x threads that saw an action outside {0, 1} (random_cartpole.py:173-174: the
+ *                    reference asserts; here the env is pushed left and the flag is raised).
+ *       counters[2]  step CTAs whose tile-ordering wait (renv_cartpole_env.progress) timed out: the progress words
+ *                    were not in the state the protocol leaves them in (see there); the step still ran.
+ *     The host reads them at its next synchronisation point and raises the reference's exception.
  *   - RNG: counter-based Philox4x32-10, key = seed, counter = (global env id, tick, purpose|slot).  `tick` is
  *     the caller's step clock (48 bits used): pass a value that grows by 1 per reset/step call and by K per
  *     K-step rollout (step k of a rollout uses tick + k).  An env starts at most one episode per tick, so
@@ -33,9 +43,12 @@
 extern "C" {
 #endif
 
-#define RENV_ABI_VERSION 4
+#define RENV_ABI_VERSION 5
 #define RENV_MAX_DIM 32          /* largest task_dim in the suite is 30 (jinja/random_humanoid.py) */
 #define RENV_NUM_STATS 6         /* episodes, sum R, sum R^2, min R, max R, sum length */
+#define RENV_TILE_ENVS_F32 1024  /* envs per step CTA: the granule of renv_cartpole_env.progress */
+#define RENV_TILE_ENVS_F64 512
+#define RENV_NUM_COUNTERS 3      /* device-detected error conditions, see `counters` below */
 
 enum renv_status {
     RENV_OK = 0,
@@ -83,6 +96,17 @@ typedef struct renv_cartpole_env {
     int32_t *elapsed;            /* (n) TimeLimit._elapsed_steps (gym 0.21)                 */
     uint32_t *episode;           /* (n) episodes started per env (statistics only; may be NULL)   */
     int32_t *beyond;             /* (n) steps_beyond_done, -1 == None (:207-222); may be NULL when auto_reset */
+    uint16_t *elapsed16;         /* (n) the same TimeLimit counter as uint16 for renv_cartpole_step_lean_f32 (16-byte
+                                    aligned); NULL otherwise.  reset zeroes whichever of elapsed / elapsed16 is set;
+                                    `elapsed` may be NULL only for an env that is stepped through the lean entry. */
+    uint32_t *progress;          /* step-to-step ordering at TILE granularity, or NULL for plain stream order.
+                                    2 * ceil(n / RENV_TILE_ENVS_F32 | _F64) uint32, 8-byte aligned, zero-initialised ONCE
+                                    by the caller and afterwards touched only by the step entry points: word 2b counts
+                                    the step CTAs that have started on tile b, word 2b+1 those that have finished.  A
+                                    step CTA runs as soon as ITS tile's previous step has finished instead of waiting
+                                    for the whole previous grid, so consecutive step launches of one stream overlap
+                                    (also under CUDA-graph replay).  All step launches that share a progress array must
+                                    be issued in one stream (or otherwise ordered), as for any in-place update. */
     int64_t n;                   /* envs in this shard */
     int64_t ld;                  /* row stride of state in elements, >= n */
     uint64_t env_id0;            /* global id of env 0 of this shard (rank * n under contiguous sharding) */
@@ -114,13 +138,23 @@ int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, u
  *   TimeLimit.step (gym 0.21; max_steps <= 0 disables)  and
  *   SyncVectorEnv auto-reset (gym 0.21; auto_reset != 0) incl. the DR resample above.
  * action (n) in {0,1}; reward (n) T; done (n) u8; truncated (n) u8 or NULL.
- * With auto_reset the state written back for a finished env is its reset state (the obs gym returns). */
+ * With auto_reset the state written back for a finished env is its reset state (the obs gym returns), and
+ * `reward` may be NULL: the reward is then 1.0 for every env on every step (:207-212) and is not written.
+ * `counters`: RENV_NUM_COUNTERS uint64 (see Conventions). */
 int renv_cartpole_step_f32(const renv_cartpole_env *env, const uint8_t *action, float *reward, uint8_t *done,
                            uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
-                           const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
+                           const renv_dr_cfg *dr, unsigned long long *counters, void *stream);
 int renv_cartpole_step_f64(const renv_cartpole_env *env, const uint8_t *action, double *reward, uint8_t *done,
                            uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
-                           const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
+                           const renv_dr_cfg *dr, unsigned long long *counters, void *stream);
+
+/* The LEAN auto-reset step: the same env-step with 54 instead of 62 bytes of HBM traffic per env (fp32).  The
+ * TimeLimit counter is env->elapsed16 (uint16: max_steps <= 65535) and no reward is written (identically 1.0 under
+ * auto-reset, :207-212).  state, xi, done and truncated are bit-identical to renv_cartpole_step_f32 with
+ * auto_reset = 1. */
+int renv_cartpole_step_lean_f32(const renv_cartpole_env *env, const uint8_t *action, uint8_t *done, uint8_t *truncated,
+                                int integrator, int max_steps, uint64_t tick, const renv_dr_cfg *dr,
+                                unsigned long long *counters, void *stream);
 
 /* Observation noise of the suite's "Noisy" env variants (jinja/random_hopper.py:28,107-108, random_half_cheetah.py,
  * random_walker2d.py:139-140, random_humanoid.py:193-204): every observation -- after a step and after a reset --
@@ -139,11 +173,11 @@ int renv_cartpole_reset_noisy_f64(const renv_cartpole_env *env, const renv_obs_n
                                   uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations, void *stream);
 int renv_cartpole_step_noisy_f32(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action,
                                  float *reward, uint8_t *done, uint8_t *truncated, int integrator, int max_steps,
-                                 int auto_reset, uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations,
+                                 int auto_reset, uint64_t tick, const renv_dr_cfg *dr, unsigned long long *counters,
                                  void *stream);
 int renv_cartpole_step_noisy_f64(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action,
                                  double *reward, uint8_t *done, uint8_t *truncated, int integrator, int max_steps,
-                                 int auto_reset, uint64_t tick, const renv_dr_cfg *dr, unsigned long long *violations,
+                                 int auto_reset, uint64_t tick, const renv_dr_cfg *dr, unsigned long long *counters,
                                  void *stream);
 
 /* K fused steps with the linear policy a = [w.s + b > 0] evaluated in-kernel, auto-reset always on.
@@ -172,12 +206,6 @@ int renv_cartpole_rollout_noisy_f64(const renv_cartpole_env *env, const renv_obs
  * (env_id >> 7, tick = step). */
 int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step,
                            void *stream);
-
-/* Micro-benchmarks used by bench.py for the rollout's compute roofline: a dependent-FMA chain with
- * `ilp` independent accumulators per thread; out (blocks*threads) keeps the result live.
- * FLOPs = 2 * blocks * threads * ilp * iters. */
-int renv_fma_peak_f32(float *out, int blocks, int threads, int iters, void *stream);
-int renv_fma_peak_f64(double *out, int blocks, int threads, int iters, void *stream);
 
 #ifdef __cplusplus
 }

@@ -9,9 +9,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RENV_B200_LIB", os.path.join(_HERE, "librenv_b200.so"))   # override: kernel experiments
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_DIM = 32
 NUM_STATS = 6
+COUNTER_GAUSSIAN, COUNTER_BAD_ACTION, COUNTER_ORDER_TIMEOUT = 0, 1, 2
+TILE_ENVS = {'float32': 1024, 'float64': 512}      # RENV_TILE_ENVS_F32 / _F64
+NUM_COUNTERS = 3          # [0] gaussian draws exhausted, [1] invalid actions (include/renv.h)
 
 OK = 0
 DR_NONE, DR_UNIFORM, DR_TRUNCNORM, DR_GAUSSIAN, DR_FULLGAUSSIAN = 0, 1, 2, 3, 4
@@ -30,7 +33,8 @@ class DrCfg(ctypes.Structure):
 class CartpoleEnv(ctypes.Structure):
     """struct renv_cartpole_env (include/renv.h)."""
     _fields_ = [("state", ctypes.c_void_p), ("xi", ctypes.c_void_p), ("elapsed", ctypes.c_void_p),
-                ("episode", ctypes.c_void_p), ("beyond", ctypes.c_void_p),
+                ("episode", ctypes.c_void_p), ("beyond", ctypes.c_void_p), ("elapsed16", ctypes.c_void_p),
+                ("progress", ctypes.c_void_p),
                 ("n", ctypes.c_int64), ("ld", ctypes.c_int64),
                 ("env_id0", ctypes.c_uint64), ("seed", ctypes.c_uint64)]
 
@@ -54,6 +58,7 @@ SIGNATURES = {
     "renv_cartpole_reset_f64": (_int, [_env_p, _vp, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_step_f32": (_int, [_env_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_step_f64": (_int, [_env_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
+    "renv_cartpole_step_lean_f32": (_int, [_env_p, _vp, _vp, _vp, _int, _int, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_reset_noisy_f32": (_int, [_env_p, _noise_p, _vp, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_reset_noisy_f64": (_int, [_env_p, _noise_p, _vp, _u64, _cfg_p, _vp, _vp]),
     "renv_cartpole_step_noisy_f32": (_int, [_env_p, _noise_p, _vp, _vp, _vp, _vp, _int, _int, _int, _u64, _cfg_p, _vp, _vp]),
@@ -63,8 +68,6 @@ SIGNATURES = {
     "renv_cartpole_rollout_noisy_f32": (_int, [_env_p, _noise_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_cartpole_rollout_noisy_f64": (_int, [_env_p, _noise_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_random_actions_u8": (_int, [_vp, _i64, _u64, _u64, _u32, _vp]),
-    "renv_fma_peak_f32": (_int, [_vp, _int, _int, _int, _vp]),
-    "renv_fma_peak_f64": (_int, [_vp, _int, _int, _int, _vp]),
 }
 
 

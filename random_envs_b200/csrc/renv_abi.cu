@@ -3,11 +3,7 @@
 #include "../../include/renv.h"
 #include "renv_kernels.cuh"
 #include "renv_rollout_pair.cuh"
-#include "renv_step_bulk.cuh"
 
-#ifndef RENV_STEP_F32_BULK
-#define RENV_STEP_F32_BULK 0        // 1: fp32 auto-reset step through cp.async.bulk tiles (renv_step_bulk.cuh)
-#endif
 #ifndef RENV_ROLLOUT_F32_PAIR
 #define RENV_ROLLOUT_F32_PAIR 1     // 0: one env per thread (scalar FFMA) for A/B timing
 #endif
@@ -50,19 +46,26 @@ template <typename T> int to_cfg4(const renv_dr_cfg *dr, DrCfg4<T> *out)
     return RENV_OK;
 }
 
-template <typename T> int check_env(const renv_cartpole_env *env, bool need_beyond, EnvPtrs<T> *out)
+enum ElapsedKind { kNeedElapsed32, kNeedElapsed16, kNeedEitherElapsed };
+template <typename T>
+int check_env(const renv_cartpole_env *env, bool need_beyond, EnvPtrs<T> *out, ElapsedKind elapsed = kNeedElapsed32)
 {
-    if (env == nullptr || env->state == nullptr || env->xi == nullptr || env->elapsed == nullptr) return RENV_E_NULL;
+    if (env == nullptr || env->state == nullptr || env->xi == nullptr) return RENV_E_NULL;
+    if (elapsed == kNeedElapsed32 && env->elapsed == nullptr) return RENV_E_NULL;
+    if (elapsed == kNeedElapsed16 && env->elapsed16 == nullptr) return RENV_E_NULL;
+    if (elapsed == kNeedEitherElapsed && env->elapsed == nullptr && env->elapsed16 == nullptr) return RENV_E_NULL;
     if (need_beyond && env->beyond == nullptr) return RENV_E_NULL;
     if (env->n <= 0 || env->ld < env->n) return RENV_E_SIZE;
     constexpr int V = VecTraits<T>::V;
     if (env->ld % V != 0) return RENV_E_ALIGN;
-    if (!aligned(env->state, 16) || !aligned(env->xi, 16) || !aligned(env->elapsed, 16) ||
-        (env->episode && !aligned(env->episode, 4)) || (env->beyond && !aligned(env->beyond, 4)))
+    if (!aligned(env->state, 16) || !aligned(env->xi, 16) || !aligned(env->elapsed, 16) || !aligned(env->elapsed16, 16) ||
+        (env->episode && !aligned(env->episode, 4)) || !aligned(env->progress, 8) || (env->beyond && !aligned(env->beyond, 4)))
         return RENV_E_ALIGN;
     out->state = static_cast<T *>(env->state);
     out->xi = static_cast<T *>(env->xi);
     out->elapsed = env->elapsed;
+    out->elapsed16 = env->elapsed16;
+    out->progress = env->progress;
     out->episode = env->episode;
     out->beyond = env->beyond;
     out->n = env->n;
@@ -181,7 +184,7 @@ int cartpole_reset(const renv_cartpole_env *env, const renv_obs_noise *noise, co
                    const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
 {
     ResetArgs<T> a;
-    int rc = check_env<T>(env, false, &a.env);
+    int rc = check_env<T>(env, false, &a.env, kNeedEitherElapsed);
     if (rc) return rc;
     rc = attach_noise<T>(noise, &a.env);
     if (rc) return rc;
@@ -196,55 +199,36 @@ int cartpole_reset(const renv_cartpole_env *env, const renv_obs_noise *noise, co
     return launch_status();
 }
 
-// fp32 auto-reset step through bulk-async tiles: full 1024-env tiles by the bulk kernel, the remainder by the LDG/STG one
-int launch_step_bulk(const StepArgs<double> &, cudaStream_t) { return RENV_E_ARG; }
-int launch_step_bulk(const StepArgs<float> &a, cudaStream_t st)
-{
-    const int64_t tiles = a.env.n / kBulkTile, rest = a.env.n - tiles * kBulkTile;
-    if (tiles > 0x7fffffffLL) return RENV_E_SIZE;
-    if (tiles > 0) cartpole_step_bulk_kernel<<<(unsigned)tiles, kBulkThreads, 0, st>>>(a);
-    if (rest > 0) {
-        StepArgs<float> r = a;
-        const int64_t i0 = tiles * kBulkTile;
-        r.env.state += i0; r.env.xi += 4 * i0; r.env.elapsed += i0;
-        if (r.env.episode) r.env.episode += i0;
-        if (r.env.beyond) r.env.beyond += i0;
-        r.env.n = rest; r.env.env_id0 += (uint64_t)i0;
-        r.action += i0; r.reward += i0; r.done += i0;
-        if (r.truncated) r.truncated += i0;
-        const int64_t blocks = (rest + kStepThreads * 4 - 1) / (kStepThreads * 4);
-        cartpole_step_kernel<float, true, false><<<(unsigned)blocks, kStepThreads, 0, st>>>(r);
-    }
-    return launch_status();
-}
-
-template <typename T>
+template <typename T, bool kLean>
 int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action, T *reward,
                   uint8_t *done, uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
-                  const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
+                  const renv_dr_cfg *dr, unsigned long long *counters, void *stream)
 {
     StepArgs<T> a;
-    int rc = check_env<T>(env, !auto_reset, &a.env);
+    int rc = check_env<T>(env, !auto_reset, &a.env, kLean ? kNeedElapsed16 : kNeedElapsed32);
     if (rc) return rc;
     rc = attach_noise<T>(noise, &a.env);
     if (rc) return rc;
-    if (action == nullptr || reward == nullptr || done == nullptr) return RENV_E_NULL;
+    if (action == nullptr || done == nullptr) return RENV_E_NULL;
+    if (reward == nullptr && !auto_reset) return RENV_E_NULL;      // only the auto-reset reward is the constant 1.0
     if (!aligned(action, 4) || !aligned(reward, 16) || !aligned(done, 4) || (truncated && !aligned(truncated, 4)))
         return RENV_E_ALIGN;
+    if (counters && !aligned(counters, 8)) return RENV_E_ALIGN;
     if (integrator != RENV_EULER && integrator != RENV_SEMI_IMPLICIT) return RENV_E_INTEGRATOR;
+    if (kLean && max_steps > 65535) return RENV_E_SIZE;
     rc = to_cfg4<T>(auto_reset ? dr : nullptr, &a.dr);
     if (rc) return rc;
     a.action = action; a.reward = reward; a.done = done; a.truncated = truncated;
     a.euler = integrator == RENV_EULER;
     a.max_steps = max_steps;
     a.tick = tick;
-    a.violations = violations;
+    a.counters = counters;
     constexpr int64_t per_block = (int64_t)kStepThreads * VecTraits<T>::V;
     const int64_t blocks = (env->n + per_block - 1) / per_block;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool noisy = a.env.obs != nullptr;
-    if (RENV_STEP_F32_BULK && sizeof(T) == 4 && auto_reset && !noisy) return launch_step_bulk(a, st);
+    if (kLean) return launch_pdl(cartpole_step_kernel<T, true, false, true>, (unsigned)blocks, kStepThreads, st, a);
     if (auto_reset && !noisy) return launch_pdl(cartpole_step_kernel<T, true, false>, (unsigned)blocks, kStepThreads, st, a);
     if (auto_reset) return launch_pdl(cartpole_step_kernel<T, true, true>, (unsigned)blocks, kStepThreads, st, a);
     if (!noisy) return launch_pdl(cartpole_step_kernel<T, false, false>, (unsigned)blocks, kStepThreads, st, a);
@@ -325,14 +309,6 @@ int cartpole_rollout(const renv_cartpole_env *env, const renv_obs_noise *noise, 
     return launch_rollout(a, static_cast<cudaStream_t>(stream));
 }
 
-template <typename T> int fma_peak(T *out, int blocks, int threads, int iters, void *stream)
-{
-    if (out == nullptr) return RENV_E_NULL;
-    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0) return RENV_E_SIZE;
-    fma_peak_kernel<T><<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(out, iters);
-    return launch_status();
-}
-
 }  // namespace
 
 extern "C" {
@@ -378,16 +354,23 @@ int renv_cartpole_reset_f64(const renv_cartpole_env *env, const uint8_t *mask, u
 
 int renv_cartpole_step_f32(const renv_cartpole_env *env, const uint8_t *action, float *reward, uint8_t *done,
                            uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
-                           const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
+                           const renv_dr_cfg *dr, unsigned long long *counters, void *stream)
 {
-    return cartpole_step<float>(env, nullptr, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
-                                dr, violations, stream);
+    return cartpole_step<float, false>(env, nullptr, action, reward, done, truncated, integrator, max_steps, auto_reset,
+                                       tick, dr, counters, stream);
+}
+int renv_cartpole_step_lean_f32(const renv_cartpole_env *env, const uint8_t *action, uint8_t *done, uint8_t *truncated,
+                                int integrator, int max_steps, uint64_t tick, const renv_dr_cfg *dr,
+                                unsigned long long *counters, void *stream)
+{
+    return cartpole_step<float, true>(env, nullptr, action, nullptr, done, truncated, integrator, max_steps, 1, tick, dr,
+                                      counters, stream);
 }
 int renv_cartpole_step_f64(const renv_cartpole_env *env, const uint8_t *action, double *reward, uint8_t *done,
                            uint8_t *truncated, int integrator, int max_steps, int auto_reset, uint64_t tick,
                            const renv_dr_cfg *dr, unsigned long long *violations, void *stream)
 {
-    return cartpole_step<double>(env, nullptr, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
+    return cartpole_step<double, false>(env, nullptr, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
                                  dr, violations, stream);
 }
 
@@ -409,7 +392,7 @@ int renv_cartpole_step_noisy_f32(const renv_cartpole_env *env, const renv_obs_no
                                  void *stream)
 {
     if (noise == nullptr) return RENV_E_NULL;
-    return cartpole_step<float>(env, noise, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
+    return cartpole_step<float, false>(env, noise, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
                                 dr, violations, stream);
 }
 int renv_cartpole_step_noisy_f64(const renv_cartpole_env *env, const renv_obs_noise *noise, const uint8_t *action,
@@ -418,7 +401,7 @@ int renv_cartpole_step_noisy_f64(const renv_cartpole_env *env, const renv_obs_no
                                  void *stream)
 {
     if (noise == nullptr) return RENV_E_NULL;
-    return cartpole_step<double>(env, noise, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
+    return cartpole_step<double, false>(env, noise, action, reward, done, truncated, integrator, max_steps, auto_reset, tick,
                                  dr, violations, stream);
 }
 
@@ -460,15 +443,6 @@ int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
     random_actions_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(action, n, env_id0, seed, step);
     return launch_status();
-}
-
-int renv_fma_peak_f32(float *out, int blocks, int threads, int iters, void *stream)
-{
-    return fma_peak<float>(out, blocks, threads, iters, stream);
-}
-int renv_fma_peak_f64(double *out, int blocks, int threads, int iters, void *stream)
-{
-    return fma_peak<double>(out, blocks, threads, iters, stream);
 }
 
 }  // extern "C"

@@ -16,12 +16,14 @@ namespace renv {
 template <typename T> struct VecTraits;
 template <> struct VecTraits<float> {
     static constexpr int V = 4;
-    using Real = float4; using Int = int4; using Byte = uchar4;
+    using Real = float4; using Int = int4; using Byte = uchar4; using Half = ushort4;
 };
 template <> struct VecTraits<double> {
     static constexpr int V = 2;
-    using Real = double2; using Int = int2; using Byte = uchar2;
+    using Real = double2; using Int = int2; using Byte = uchar2; using Half = ushort2;
 };
+
+__device__ __forceinline__ bool full_tile(int64_t block0, int64_t n, int tile) { return block0 + tile <= n; }
 
 template <typename Vec, typename S, int V> __device__ __forceinline__ void vload(S (&dst)[V], const S *src)
 {
@@ -65,29 +67,31 @@ __device__ __forceinline__ void store_xi(double *xi, int64_t i, const Xi<double>
 
 template <typename T> struct EnvPtrs {
     T *state; T *xi; int32_t *elapsed; uint32_t *episode; int32_t *beyond;
+    uint16_t *elapsed16;      // lean step only: the TimeLimit counter as uint16 (then `elapsed` may be nullptr)
+    uint32_t *progress;       // tile-granular step ordering (see cartpole_step_kernel); nullptr: the stream orders steps
     int64_t n, ld; uint64_t env_id0, seed;
     T *obs; T noise_std;      // "Noisy" variants: obs (4, ld) = state + noise_std * N(0, I); obs == nullptr: obs IS state
 };
 
 // RandomCartPoleEnv.reset (+ set_random_task) of env i at clock `tick`; scalar stores.
 template <typename T>
-__device__ __forceinline__ unsigned reset_env(const EnvPtrs<T> &env, const DrCfg4<T> &dr, int64_t i, uint64_t tick)
+__device__ __forceinline__ unsigned reset_env(const EnvPtrs<T> &env, const DrCfg4<T> &dr, int64_t i, uint64_t tick, uint64_t seed)
 {
     const int64_t ld = env.ld;
     const uint64_t id = env.env_id0 + (uint64_t)i;
     State<T> st;
-    init_state(st, env.seed, id, tick);
+    init_state(st, seed, id, tick);
     env.state[0 * ld + i] = st.x; env.state[1 * ld + i] = st.x_dot;
     env.state[2 * ld + i] = st.theta; env.state[3 * ld + i] = st.theta_dot;
     if (env.obs) {                                         // noisy observation of the reset state (_get_obs in reset_model)
         T o[4];
-        add_obs_noise(st, env.noise_std, env.seed, id, tick, 1u, o);
+        add_obs_noise(st, env.noise_std, seed, id, tick, 1u, o);
         env.obs[0 * ld + i] = o[0]; env.obs[1 * ld + i] = o[1]; env.obs[2 * ld + i] = o[2]; env.obs[3 * ld + i] = o[3];
     }
     unsigned viol = 0;
     if (dr.dr_type != kDrNone) {
         Xi<T> xi = { T(0), T(0), T(0), T(0) };
-        viol = sample_xi(xi, dr, env.seed, id, tick);
+        viol = sample_xi(xi, dr, seed, id, tick);
         store_xi(env.xi, i, xi);
     }
     if (env.episode) atomicAdd(env.episode + i, 1u);      // optional episode count: fire-and-forget RED, no load stall
@@ -97,42 +101,125 @@ __device__ __forceinline__ unsigned reset_env(const EnvPtrs<T> &env, const DrCfg
 // ------------------------------------------------------------------------------------------------
 // Single step: RandomCartPoleEnv.step + TimeLimit.step + SyncVectorEnv auto-reset (+ set_random_task)
 // ------------------------------------------------------------------------------------------------
+// Device counters the host checks at its next synchronisation point (include/renv.h RENV_NUM_COUNTERS).
+enum Counter : int { kCounterGaussian = 0, kCounterBadAction = 1, kCounterOrderTimeout = 2 };
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// L2 prefetch of a contiguous span (1-D bulk form: one instruction, no register or shared-memory destination).
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+#ifndef RENV_ORDER_SPINS
+#define RENV_ORDER_SPINS (1 << 21)      // x ~40 ns: ~0.1 s, then the CTA proceeds and raises kCounterOrderTimeout
+#endif
+#ifndef RENV_TILE_PREFETCH
+#define RENV_TILE_PREFETCH 1
+#endif
+
 template <typename T> struct StepArgs {
     EnvPtrs<T> env;
     const uint8_t *action; T *reward; uint8_t *done; uint8_t *truncated;
     int euler, max_steps;
     uint64_t tick;
     DrCfg4<T> dr;
-    unsigned long long *violations;
+    unsigned long long *counters;   // [kCounterGaussian], [kCounterBadAction]; may be nullptr
 };
 
 #ifndef RENV_STEP_THREADS
 #define RENV_STEP_THREADS 256
 #endif
 constexpr int kStepThreads = RENV_STEP_THREADS;
+#ifndef RENV_STEP_MIN_CTAS
+#define RENV_STEP_MIN_CTAS(T) ((sizeof(T) == 4 ? 4 : 3) * 256 / kStepThreads)
+#endif
 
+// Tiles a CTA may own in one launch (tickets are kept in shared memory); the launcher sizes the grid accordingly.
 // kAutoReset = true is the hot kernel.  Finished envs are NOT reset by the thread that owns them (that would
 // run the ~250-instruction Philox/sampling path once per warp per finished lane with ~1 active lane): their
 // CTA-local indices are appended to a shared-memory list and, after one __syncthreads, the first `count`
 // threads of the CTA each reset one env at full lane utilisation, overwriting the owner's stores.
-template <typename T, bool kAutoReset, bool kNoisy = false>
-__global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 / kStepThreads) cartpole_step_kernel(const __grid_constant__ StepArgs<T> a)
+//
+// kLean (auto-reset only): the TimeLimit counter is a.env.elapsed16 (uint16: 2 + 2 B instead of 4 + 4 B per env-step); the
+// reward -- identically 1.0 under auto-reset, random_cartpole.py:207-212 -- is not written when a.reward == nullptr
+// (any variant).  Together: 54 instead of 62 B per fp32 env-step.  State / done / truncated are bit-identical.
+//
+// Ordering between consecutive steps of one stream (a tile = one CTA = kStepThreads * V consecutive envs):
+//
+// (a) env.progress == nullptr: GRID-granular.  Programmatic dependent launch (the launcher sets
+//     cudaLaunchAttributeProgrammaticStreamSerialization): griddepcontrol.wait -- before the first global access -- until
+//     the PREVIOUS grid of the stream has completed and flushed; further down this grid lets the NEXT one be scheduled
+//     into SM slots as it drains.  No-ops without the attribute.
+// (b) env.progress != nullptr: TILE-granular.  A step of env i depends on the previous step of env i and on nothing
+//     else, so the grid-wide wait is replaced by two words per tile:
+//         progress[2 b]      tickets handed out for tile b   (atomicAdd at CTA entry)
+//         progress[2 b + 1]  steps completed on tile b       (st.release after the CTA's last store)
+//     CTA b takes ticket t and steps its tile as soon as progress[2 b + 1] == t.  The ticket is taken BEFORE the CTA
+//     executes griddepcontrol.launch_dependents and the next grid of the stream cannot start before every CTA of this
+//     one has done so, hence tickets follow launch order; and every predecessor CTA is resident or finished when a
+//     CTA spins, hence no deadlock.  Kernels of the same stream then overlap: the ~2.3 us launch-to-launch bubble of
+//     (a) (drain + flush + first DRAM round trip) shrinks to the CTA's own ticket round trip, during which the tile is
+//     pulled from HBM into L2 by bulk prefetches (UBLKPF: no registers, no shared memory), and steps of DIFFERENT env
+//     batches issued round-robin on one stream do not wait for each other at all.  The grid-wide wait moves to the
+//     END of the CTA, so that this grid cannot complete before its predecessor has (anything launched after it without
+//     the PDL attribute still sees every earlier step finished).  Works unchanged under CUDA-graph replay (nothing
+//     about launch order is baked into the launch).
+//     Measured (B200, 4 x 2^20 envs round-robin on ONE stream, profiles/exp/r2_step_ring/): 13.4 -> 12.1 us per launch;
+//     on 4 parallel graph branches or at 2^24 envs, where (a) has no bubble to lose, the ticket round trip costs 5 %
+//     -- the host picks the mode by size.  Also measured there and NOT adopted: a persistent one-CTA-per-SM kernel
+//     streaming tiles through a shared-memory ring with cp.async.bulk (12.1 us in the best of 15 configurations, one
+//     of which hung), and CTAs that step 2 or 4 tiles (a loop makes ptxas spill the freshly loaded rows; straight-line
+//     copies blow the instruction cache: 16 us).
+template <typename T, bool kAutoReset, bool kNoisy = false, bool kLean = false>
+__global__ void __launch_bounds__(kStepThreads, RENV_STEP_MIN_CTAS(T)) cartpole_step_kernel(const __grid_constant__ StepArgs<T> a)
 {
     using VT = VecTraits<T>;
     constexpr int V = VT::V;
+    constexpr int kTile = kStepThreads * V;
     __shared__ unsigned s_count;
-    __shared__ uint16_t s_list[kAutoReset ? kStepThreads * V : 1];
-    const int64_t block0 = (int64_t)blockIdx.x * (kStepThreads * V);
+    __shared__ uint16_t s_list[kAutoReset ? kTile : 1];
+    const int64_t block0 = (int64_t)blockIdx.x * kTile;
     const int64_t i0 = block0 + (int64_t)threadIdx.x * V;
     const int64_t n = a.env.n, ld = a.env.ld;
     const bool live = i0 < n;
     const bool full = i0 + V <= n;
+    const bool tracked = a.env.progress != nullptr;
+    uint32_t ticket = 0;
 
-    // Programmatic dependent launch (the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization): wait here
-    // -- before the first global access -- until the PREVIOUS grid of the stream has completed and flushed; further
-    // down this grid lets the NEXT one be scheduled into SM slots as it drains.  Back-to-back steps of one stream
-    // then lose most of the ~1.5 us launch/ramp gap between 11 us kernels.  No-ops without the attribute.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tracked) {
+        if (threadIdx.x == 0) {
+            uint32_t *const slot = a.env.progress + 2 * (size_t)blockIdx.x;
+            ticket = atomicAdd(slot, 1u);
+            uint32_t seen = ld_acquire_gpu(slot + 1);
+            for (int spin = 0; seen != ticket && spin < RENV_ORDER_SPINS; ++spin) {     // rare: the predecessor is still on this tile
+                __nanosleep(32);
+                seen = ld_acquire_gpu(slot + 1);
+            }
+            if (seen != ticket && a.counters) atomicAdd(a.counters + kCounterOrderTimeout, 1ull);
+            if (kAutoReset) s_count = 0;
+        } else if (RENV_TILE_PREFETCH && block0 + kTile <= n && threadIdx.x >= 32 && threadIdx.x < 39) {
+            // while thread 0 waits for its L2 round trip the tile is pulled from HBM into L2 (never stale: L2 is the
+            // point of coherence), so the loads below pay an L2 hit instead of a second DRAM latency
+            const int q = threadIdx.x - 32;
+            if (q < 4) prefetch_l2(a.env.state + q * ld + block0, kTile * sizeof(T));
+            else if (q == 4) prefetch_l2(a.env.xi + 4 * block0, kTile * 4 * sizeof(T));
+            else if (q == 5) { if (kLean) prefetch_l2(a.env.elapsed16 + block0, kTile * 2); else prefetch_l2(a.env.elapsed + block0, kTile * 4); }
+            else prefetch_l2(a.action + block0, kTile);
+        }
+        __syncthreads();            // thread 0 holds the ticket and has seen the predecessor's release
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     T s[4][V];
     Xi<T> p[V];
@@ -143,10 +230,17 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 /
         for (int c = 0; c < 4; ++c) vload<typename VT::Real>(s[c], a.env.state + c * ld + i0);
 #pragma unroll
         for (int v = 0; v < V; ++v) p[v] = load_xi(a.env.xi, i0 + v);
-        vload<typename VT::Int>(el, a.env.elapsed + i0);
+        if (kLean) {
+            uint16_t e16[V];
+            vload<typename VT::Half>(e16, a.env.elapsed16 + i0);
+#pragma unroll
+            for (int v = 0; v < V; ++v) el[v] = e16[v];
+        } else {
+            vload<typename VT::Int>(el, a.env.elapsed + i0);
+        }
         vload<typename VT::Byte>(act, a.action + i0);
     }
-    if (kAutoReset) {
+    if (kAutoReset && !tracked) {
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();            // overlaps the loads' latency
     }
@@ -159,7 +253,7 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 /
 #pragma unroll
                 for (int c = 0; c < 4; ++c) s[c][v] = ok ? a.env.state[c * ld + i0 + v] : T(0);
                 p[v] = ok ? load_xi(a.env.xi, i0 + v) : Xi<T>{ T(1), T(1), T(1), T(1) };
-                el[v] = ok ? a.env.elapsed[i0 + v] : 0;
+                el[v] = !ok ? 0 : kLean ? (int32_t)a.env.elapsed16[i0 + v] : a.env.elapsed[i0 + v];
                 act[v] = ok ? a.action[i0 + v] : 0;
             }
         }
@@ -167,8 +261,10 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 /
         T rew[V];
         uint8_t dn[V], tr[V];
         const bool euler = a.euler != 0;
+        bool bad_action = false;            // Discrete(2).contains (:173-174): the host raises at its next sync
 #pragma unroll
         for (int v = 0; v < V; ++v) {
+            bad_action = bad_action || act[v] > 1;
             State<T> st = { s[0][v], s[1][v], s[2][v], s[3][v] };
             const bool terminated = dynamics(st, p[v], derive(p[v]), act[v], euler);
             s[0][v] = st.x; s[1][v] = st.x_dot; s[2][v] = st.theta; s[3][v] = st.theta_dot;
@@ -187,6 +283,7 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 /
                 s_list[atomicAdd(&s_count, 1u)] = (uint16_t)(threadIdx.x * V + v);
             }
         }
+        if (bad_action && a.counters) atomicAdd(a.counters + kCounterBadAction, 1ull);
 
         if (kNoisy) {       // obs = new state + std * N(0, I); a finished env's obs is overwritten by its reset below
             T o[4][V];
@@ -211,16 +308,22 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 /
             }
         }
 
-        // Trigger AFTER the arithmetic: the dependent grid becomes launchable when every CTA of this one is about
+        // (a): trigger AFTER the arithmetic: the dependent grid becomes launchable when every CTA of this one is about
         // to store, so its CTAs spin in griddepcontrol.wait only briefly.  Triggering at kernel entry was 4 % faster
-        // for one stream (eager 7.9e10 vs 7.6e10 env-steps/s) but cost the 4-independent-batch graph 1 % (0.907 vs
-        // 0.916 of the HBM peak): the early-resident waiters took SM slots from the other batches' kernels.
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        // for one stream but cost 4 independent graph branches 1 % (round 1).
+        if (!tracked) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (full) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) vstore<typename VT::Real>(a.env.state + c * ld + i0, s[c]);
-            vstore<typename VT::Int>(a.env.elapsed + i0, el);
-            vstore<typename VT::Real>(a.reward + i0, rew);
+            if (kLean) {
+                uint16_t e16[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) e16[v] = (uint16_t)el[v];
+                vstore<typename VT::Half>(a.env.elapsed16 + i0, e16);
+            } else {
+                vstore<typename VT::Int>(a.env.elapsed + i0, el);
+            }
+            if (a.reward) vstore<typename VT::Real>(a.reward + i0, rew);
             vstore<typename VT::Byte>(a.done + i0, dn);
             if (a.truncated) vstore<typename VT::Byte>(a.truncated + i0, tr);
         } else {
@@ -229,13 +332,16 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 /
                 if (i0 + v < n) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) a.env.state[c * ld + i0 + v] = s[c][v];
-                    a.env.elapsed[i0 + v] = el[v];
-                    a.reward[i0 + v] = rew[v];
+                    if (kLean) a.env.elapsed16[i0 + v] = (uint16_t)el[v];
+                    else a.env.elapsed[i0 + v] = el[v];
+                    if (a.reward) a.reward[i0 + v] = rew[v];
                     a.done[i0 + v] = dn[v];
                     if (a.truncated) a.truncated[i0 + v] = tr[v];
                 }
             }
         }
+    } else if (!tracked) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
 
     if (kAutoReset) {
@@ -243,8 +349,15 @@ __global__ void __launch_bounds__(kStepThreads, (sizeof(T) == 4 ? 4 : 3) * 256 /
         const unsigned count = s_count;
         unsigned viol = 0;
         for (unsigned j = threadIdx.x; j < count; j += kStepThreads)
-            viol += reset_env(a.env, a.dr, block0 + s_list[j], a.tick);
-        if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
+            viol += reset_env(a.env, a.dr, block0 + s_list[j], a.tick, a.env.seed);
+        if (viol && a.counters) atomicAdd(a.counters + kCounterGaussian, (unsigned long long)viol);
+    }
+    if (tracked) {
+        __syncthreads();                    // every store of the CTA precedes (happens-before) thread 0's release
+        if (threadIdx.x == 0) {
+            st_release_gpu(a.env.progress + 2 * (size_t)blockIdx.x + 1, ticket + 1u);
+            asm volatile("griddepcontrol.wait;" ::: "memory");     // do not complete before the previous grid has
+        }
     }
 }
 
@@ -264,9 +377,10 @@ template <typename T> __global__ void __launch_bounds__(256) cartpole_reset_kern
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.env.n) return;
     if (a.mask && !a.mask[i]) return;
-    a.env.elapsed[i] = 0;
+    if (a.env.elapsed) a.env.elapsed[i] = 0;
+    if (a.env.elapsed16) a.env.elapsed16[i] = 0;
     if (a.env.beyond) a.env.beyond[i] = -1;
-    const unsigned viol = reset_env(a.env, a.dr, i, a.tick);
+    const unsigned viol = reset_env(a.env, a.dr, i, a.tick, a.env.seed);
     if (viol && a.violations) atomicAdd(a.violations, (unsigned long long)viol);
 }
 

@@ -48,7 +48,7 @@ class _MappedScalarCore:
         self.beyond, self.reward, self.done, self.action = (k["beyond"].numpy(), k["reward"].numpy(), k["done"].numpy(),
                                                             k["action"].numpy())
         self.beyond[:] = -1
-        self.viol = t.zeros(1, dtype=t.int64, device=self.device)
+        self.viol = t.zeros(_lib.NUM_COUNTERS, dtype=t.int64, device=self.device)
         env = _lib.CartpoleEnv()
         env.state, env.xi, env.elapsed = k["state"].data_ptr(), k["xi"].data_ptr(), k["elapsed"].data_ptr()
         env.episode, env.beyond = None, k["beyond"].data_ptr()

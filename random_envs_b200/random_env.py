@@ -22,6 +22,8 @@ from .gym_compat import Env
 SAMPLING_UNSET_MSG = ("sampling value of random env needs to be set before using sample_task() or "
                       "set_random_task(). Set it by uploading a DR distr.")
 GAUSSIAN_FAIL_MSG = "Not all samples were above > 0.1 after 2 attempts"
+INVALID_ACTION_MSG = ("an action outside Discrete(2) was passed to step(): the reference asserts '%r (%s) invalid' "
+                      "(random_cartpole.py:173-174); detected on the device, the affected envs were pushed left")
 
 
 def covariance_factor(cov):
@@ -48,7 +50,7 @@ class RandomEnv(Env):
         self.dyn_ind_to_name = None
         self._dr_seed = 0
         self._dr_calls = 0
-        self._dr_violations = None     # device int64 counter, allocated on first GPU use
+        self._dr_violations = None     # device int64[NUM_COUNTERS] (include/renv.h `counters`), allocated on first GPU use
 
     # ---- hooks every env overrides (random_env.py:20-34) ----------------------------------------
     def get_search_bounds_mean(self, index):
@@ -186,17 +188,28 @@ class RandomEnv(Env):
     def _violation_counter(self, device):
         t = _device.torch()
         if self._dr_violations is None or self._dr_violations.device != device:
-            self._dr_violations = t.zeros(1, dtype=t.int64, device=device)
+            self._dr_violations = t.zeros(_lib.NUM_COUNTERS, dtype=t.int64, device=device)
         return self._dr_violations
 
     def check_dr_violations(self):
         """Raise the reference's gaussian failure if any device-side draw exhausted its 3 attempts."""
-        if self._dr_violations is not None and int(self._dr_violations.item()) != 0:
+        if self._dr_violations is None:
+            return
+        gaussian, bad_action, order_timeout = (int(v) for v in self._dr_violations.tolist())
+        if gaussian or bad_action or order_timeout:
             self._dr_violations.zero_()
+        if order_timeout:
+            raise RuntimeError("%d step CTAs timed out waiting for their tile's previous step (renv_cartpole_env.progress "
+                               "was modified outside the step kernels, or steps sharing it ran unordered)" % order_timeout)
+        if bad_action:
+            raise AssertionError(INVALID_ACTION_MSG)
+        if gaussian:
             raise Exception(GAUSSIAN_FAIL_MSG)
 
-    def sample_tasks_tensor(self, num_tasks=1, dtype=None, device=None, out=None):
-        """``sample_tasks`` without leaving the GPU: returns a (num_tasks, task_dim) CUDA tensor."""
+    def sample_tasks_tensor(self, num_tasks=1, dtype=None, device=None, out=None, sample_id0=0):
+        """``sample_tasks`` without leaving the GPU: returns a (num_tasks, task_dim) CUDA tensor.  Row i is keyed by
+        (seed_dr seed, sample_id0 + i, call index): a rank that owns global envs [id0, id0 + n) passes sample_id0=id0
+        and draws exactly the rows the unsharded call would."""
         if self.sampling is None:
             raise ValueError(SAMPLING_UNSET_MSG)
         t = _device.torch()
@@ -209,14 +222,23 @@ class RandomEnv(Env):
         fn = {t.float32: "renv_dr_sample_f32", t.float64: "renv_dr_sample_f64"}[dtype]
         viol = self._violation_counter(dev)
         with t.cuda.device(dev):
-            _lib.call(fn, _device.ptr(out), num_tasks, cfg, self._dr_seed, 0, self._dr_calls, _device.ptr(viol),
+            _lib.call(fn, _device.ptr(out), num_tasks, cfg, self._dr_seed, int(sample_id0), self._dr_calls, _device.ptr(viol),
                       _device.stream_ptr(dev))
         self._dr_calls = (self._dr_calls + 1) & 0xFFFFFFFF
         return out
 
     def sample_tasks(self, num_tasks=1):
-        out = self.sample_tasks_tensor(num_tasks, dtype=_device.torch().float64).cpu().numpy()
-        self.check_dr_violations()
+        t = _device.torch()
+        before = None
+        if self._dr_violations is not None:         # violations of EARLIER launches are not this call's: keep them apart
+            before = self._dr_violations.clone()
+            self._dr_violations.zero_()
+        try:
+            out = self.sample_tasks_tensor(num_tasks, dtype=t.float64).cpu().numpy()
+            self.check_dr_violations()
+        finally:
+            if before is not None:
+                self._dr_violations += before
         return out
 
     def sample_task(self):

@@ -45,7 +45,8 @@ class RandomCartPoleVecEnv(RandomEnv):
 
     def __init__(self, num_envs, dtype="float32", device=None, seed=0, env_id0=0,
                  max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, kinematics_integrator="euler",
-                 track_truncated=True, validate_actions=False, track_episodes=True, noisy=False, noise_level=1e-4):
+                 track_truncated=True, validate_actions=True, track_episodes=True, noisy=False, noise_level=1e-4,
+                 lean=False, tile_ordering="auto"):
         RandomEnv.__init__(self)
         if num_envs <= 0:
             raise ValueError("num_envs must be positive")
@@ -67,6 +68,18 @@ class RandomCartPoleVecEnv(RandomEnv):
         self.noise_level = float(noise_level)
         if self.noise_level < 0:
             raise ValueError("noise_level must be >= 0")
+        # lean step (include/renv.h renv_cartpole_step_lean_f32): uint16 TimeLimit counter, no reward store -- 54 instead
+        # of 62 bytes of HBM traffic per env-step; state / done / truncated bit-identical
+        self.lean = bool(lean)
+        if self.lean and (self._dtype_name != "float32" or not self.auto_reset or self.noisy
+                          or not 0 < self.max_episode_steps <= 65535):
+            raise ValueError("lean=True needs float32, auto_reset, no observation noise and 0 < max_episode_steps <= 65535")
+
+        # step-to-step ordering per 1024-env tile instead of per launch (include/renv.h renv_cartpole_env.progress):
+        # consecutive step() launches of one stream overlap; False = plain stream order between launches.  "auto": on
+        # up to 2^21 envs, where the launch-to-launch bubble is >= 10 % of a step; beyond that (and for steps issued
+        # from several streams / parallel graph branches) the per-CTA ticket round trip costs more than it saves
+        self.tile_ordering = (self.num_envs <= (1 << 21)) if tile_ordering == "auto" else bool(tile_ordering)
 
         self.dyn_ind_to_name = dict(enumerate(_TABLE.names))
         self.original_task = np.array(NOMINAL_TASK)
@@ -84,6 +97,7 @@ class RandomCartPoleVecEnv(RandomEnv):
         self._cfg_cache = None
         self._cfg_key = None
         self._tick = 0                  # step clock: Philox episode key; +1 per reset/step, +K per rollout
+        self.seed_dr(self._seed)        # set_random_task / sample_tasks draw from the constructor seed's stream
 
     # ---- xi tables (random_cartpole.py:123-147) ----------------------------------------------------
     def get_search_bounds_mean(self, index):
@@ -113,15 +127,18 @@ class RandomCartPoleVecEnv(RandomEnv):
         b = dict(device=dev, ld=ld)
         b["state"] = t.zeros((4, ld), dtype=dt, device=dev)
         b["xi"] = t.tensor(NOMINAL_TASK, dtype=dt, device=dev).reshape(1, 4).repeat(ld, 1).contiguous()   # (ld, 4) rows
-        b["elapsed"] = t.zeros(ld, dtype=t.int32, device=dev)
+        b["elapsed"] = None if self.lean else t.zeros(ld, dtype=t.int32, device=dev)
+        b["elapsed16"] = t.zeros(ld, dtype=t.int16, device=dev) if self.lean else None     # uint16 bit pattern
         b["episode"] = t.zeros(ld, dtype=t.int32, device=dev)       # uint32 bit pattern
         b["beyond"] = t.full((ld,), -1, dtype=t.int32, device=dev)
-        b["reward"] = t.zeros(ld, dtype=dt, device=dev)
+        b["reward"] = t.ones(ld, dtype=dt, device=dev)      # lean: never written, 1.0 on every step (:207-212)
         b["done"] = t.zeros(ld, dtype=t.uint8, device=dev)
         b["truncated"] = t.zeros(ld, dtype=t.uint8, device=dev)
         b["action"] = t.zeros(ld, dtype=t.uint8, device=dev)
         b["stats"] = t.tensor([0.0, 0.0, 0.0, math.inf, -math.inf, 0.0], dtype=t.float64, device=dev)
         b["obs"] = t.zeros((4, ld), dtype=dt, device=dev) if self.noisy else None
+        tiles = -(-n // _lib.TILE_ENVS[self._dtype_name])
+        b["progress"] = t.zeros(2 * tiles, dtype=t.int32, device=dev) if self.tile_ordering else None
         b["env"] = None
         self._buffers = b
         self._refresh_env_struct()
@@ -131,7 +148,10 @@ class RandomCartPoleVecEnv(RandomEnv):
         b = self._buffers
         env = _lib.CartpoleEnv()
         env.state, env.xi = b["state"].data_ptr(), b["xi"].data_ptr()
-        env.elapsed, env.beyond = b["elapsed"].data_ptr(), b["beyond"].data_ptr()
+        env.elapsed = None if self.lean else b["elapsed"].data_ptr()
+        env.elapsed16 = b["elapsed16"].data_ptr() if self.lean else None
+        env.beyond = b["beyond"].data_ptr()
+        env.progress = b["progress"].data_ptr() if b["progress"] is not None else None
         env.episode = b["episode"].data_ptr() if self.track_episodes else None
         env.n, env.ld = self.num_envs, b["ld"]
         env.env_id0, env.seed = self.env_id0, self._seed
@@ -179,6 +199,7 @@ class RandomCartPoleVecEnv(RandomEnv):
             seed = int(np.random.SeedSequence().entropy % (2 ** 63))
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.seed_dr(self._seed)
+        self._tick = 0                  # the reference rebuilds np_random: seed(s); reset() repeats the same episode
         if self._buffers is not None:
             self._refresh_env_struct()
         return [seed]
@@ -216,32 +237,34 @@ class RandomCartPoleVecEnv(RandomEnv):
         t = _device.torch()
         n = self.num_envs
         if isinstance(actions, t.Tensor) and actions.is_cuda and actions.dtype == t.uint8 and actions.is_contiguous() \
-                and actions.data_ptr() % 4 == 0 and actions.numel() >= n and actions.dim() == 1:
-            staged = actions
-        else:
-            src = actions if isinstance(actions, t.Tensor) else t.as_tensor(np.asarray(actions))
-            if src.shape != (n,):
-                raise ValueError("actions must have shape (%d,), got %s" % (n, tuple(src.shape)))
-            if src.dtype.is_floating_point:
-                raise AssertionError("%r (%s) invalid" % (actions, type(actions)))   # Discrete(2) rejects floats
-            b["action"][:n].copy_(src, non_blocking=True)
-            staged = b["action"]
-        if self.validate_actions and bool((staged[:n] > 1).any().item()):
-            raise AssertionError("%r (%s) invalid" % (actions, type(actions)))
-        return staged
+                and actions.data_ptr() % 16 == 0 and actions.device == b["device"] \
+                and (tuple(actions.shape) == (n,) or actions is b["action"]):
+            return actions              # zero copy; values outside {0, 1} are flagged by the step kernel itself
+        src = actions if isinstance(actions, t.Tensor) else t.as_tensor(np.asarray(actions))
+        if tuple(src.shape) != (n,):
+            raise ValueError("actions must have shape (%d,), got %s" % (n, tuple(src.shape)))
+        if src.dtype.is_floating_point or src.dtype == t.bool:
+            raise AssertionError("%r (%s) invalid" % (actions, type(actions)))   # Discrete(2) rejects floats and bools
+        if src.dtype != t.uint8:
+            # a wider integer would be truncated to 8 bits by the staging copy: clamp so that anything outside
+            # {0, 1} stays outside (negative -> 255, large -> 255) and is caught on the device
+            src = src.to(b["device"], non_blocking=True)
+            src = t.where((src < 0) | (src > 255), t.full_like(src, 255), src)
+        b["action"][:n].copy_(src, non_blocking=True)
+        return b["action"]
 
     def _step_plan(self):
         """Everything about a ``step`` launch that does not change between calls: the bound C function, the ctypes
         pointers of the persistent buffers and the views handed back.  Rebuilt when a layout-affecting attribute
         changes.  (A 2^20-env step is an 11 us kernel: per-call Python work has to stay below that.)"""
         b = self._buffers
-        key = (self.noisy, self.track_truncated, self._dtype_name)
+        key = (self.noisy, self.track_truncated, self._dtype_name, self.lean)
         plan = b.get("step_plan")
         if plan is not None and plan["key"] == key:
             return plan
         t = _device.torch()
         n = self.num_envs
-        fn, head = self._entry("step")
+        fn, head = self._entry("step_lean" if self.lean else "step")
         info = {"TimeLimit.truncated": b["truncated"][:n].view(t.bool)} if self.track_truncated else {}
         viol = self._violation_counter(b["device"])
         plan = dict(key=key, fn=getattr(_lib.load(), fn), name=fn, head=head,
@@ -257,7 +280,13 @@ class RandomCartPoleVecEnv(RandomEnv):
         """One env-step for all N envs.  actions: (N,) integer tensor/array in {0, 1}.
 
         Returns (obs (N, 4), reward (N,), done (N,) bool, info) -- views of the env's own buffers, refreshed in place
-        by every step (as the reference's obs aliases its state, random_cartpole.py:224)."""
+        by every step (as the reference's obs aliases its state, random_cartpole.py:224).
+
+        Nothing here synchronises with the GPU, so the two errors the reference raises from inside ``step`` /
+        ``reset`` -- an action outside Discrete(2) (random_cartpole.py:173-174) and a gaussian DR draw that stayed
+        below 0.1 three times (random_env.py:181-186) -- are detected by the kernels, counted on the device and raised
+        by the next call that already synchronises: ``step_host_wait``, ``episode_stats``, ``state_dict``,
+        ``set_random_task``, ``sample_tasks`` or an explicit ``check_dr_violations()``."""
         b = self._alloc()
         t = _device.torch()
         plan = self._step_plan()
@@ -268,9 +297,13 @@ class RandomCartPoleVecEnv(RandomEnv):
         if self.noisy:
             b["noise"].std = math.sqrt(self.noise_level)
         idx = plan["device_index"]
-        args = plan["head"] + (action_ptr, plan["reward"], plan["done"], plan["truncated"],
-                               self._integrator(), self.max_episode_steps, int(self.auto_reset), self._tick,
-                               self._active_dr_cfg(), plan["viol"], ctypes.c_void_p(_device.raw_stream(idx)))
+        if self.lean:
+            args = plan["head"] + (action_ptr, plan["done"], plan["truncated"], self._integrator(), self.max_episode_steps,
+                                   self._tick, self._active_dr_cfg(), plan["viol"], ctypes.c_void_p(_device.raw_stream(idx)))
+        else:
+            args = plan["head"] + (action_ptr, plan["reward"], plan["done"], plan["truncated"],
+                                   self._integrator(), self.max_episode_steps, int(self.auto_reset), self._tick,
+                                   self._active_dr_cfg(), plan["viol"], ctypes.c_void_p(_device.raw_stream(idx)))
         if t.cuda.current_device() == idx:
             rc = plan["fn"](*args)
         else:
@@ -305,6 +338,8 @@ class RandomCartPoleVecEnv(RandomEnv):
         ``w=None``, under the random policy ``action_space.sample()`` (test_random_policy.py:26)."""
         buf = self._alloc()
         t = _device.torch()
+        if self.lean:
+            raise ValueError("rollout() keeps the int32 TimeLimit counter: build the env without lean=True")
         if w is None:         # random policy: the fused equivalent of K x step(sample_actions())
             if self.noisy:
                 raise ValueError("the random policy ignores observations: use a noise-free env")
@@ -330,7 +365,16 @@ class RandomCartPoleVecEnv(RandomEnv):
 
     def episode_stats(self):
         from .distributed import summarize_stats
-        return summarize_stats(self.stats_tensor.cpu().numpy())
+        stats = self.stats_tensor.cpu().numpy()         # synchronises: the deferred device-side errors surface here
+        self.check_dr_violations()
+        return summarize_stats(stats)
+
+    def check_dr_violations(self):
+        """Raise what the reference would have raised inside step()/reset() (see ``step``); ``validate_actions=False``
+        silences the invalid-action assertion (the device flag is then cleared unseen)."""
+        if not self.validate_actions and self._dr_violations is not None:
+            self._dr_violations[_lib.COUNTER_BAD_ACTION] = 0
+        RandomEnv.check_dr_violations(self)
 
     # ---- tasks --------------------------------------------------------------------------------------
     def get_task(self):
@@ -356,7 +400,10 @@ class RandomCartPoleVecEnv(RandomEnv):
 
     def set_random_task(self):
         """Resample xi of every env now (random_env.py:37-39)."""
-        self.set_task(self.sample_tasks_tensor(self.num_envs, dtype=self.torch_dtype, device=self._alloc()["device"]))
+        # sample i of the call is keyed by the GLOBAL env id, so a sharded env draws what the unsharded one would
+        self.set_task(self.sample_tasks_tensor(self.num_envs, dtype=self.torch_dtype, device=self._alloc()["device"],
+                                               sample_id0=self.env_id0))
+        self.check_dr_violations()
 
     # ---- host-buffer entry point (end-to-end path: H2D actions, D2H results) -------------------------
     def host_buffers(self):
@@ -370,7 +417,8 @@ class RandomCartPoleVecEnv(RandomEnv):
                      state=t.empty((4, b["ld"]), dtype=self.torch_dtype).pin_memory(),
                      reward=t.empty(b["ld"], dtype=self.torch_dtype).pin_memory(),
                      done=t.empty(b["ld"], dtype=t.uint8).pin_memory(),
-                     truncated=t.empty(b["ld"], dtype=t.uint8).pin_memory())
+                     truncated=t.empty(b["ld"], dtype=t.uint8).pin_memory(),
+                     counters=t.zeros(_lib.NUM_COUNTERS, dtype=t.int64).pin_memory())
             h["np"] = dict(action=h["action"].numpy()[:n], obs=h["state"].numpy()[:, :n].T,
                            reward=h["reward"].numpy()[:n], done=h["done"].numpy()[:n].view(np.bool_),
                            truncated=h["truncated"].numpy()[:n].view(np.bool_))
@@ -393,7 +441,12 @@ class RandomCartPoleVecEnv(RandomEnv):
         h = b["host"]
         t = _device.torch()
         if actions is not None:
-            np.copyto(views["action"], np.asarray(actions), casting="unsafe")
+            acts = np.asarray(actions)
+            if acts.dtype != np.uint8:
+                if acts.dtype.kind not in "iu":
+                    raise AssertionError("%r (%s) invalid" % (actions, type(actions)))   # Discrete(2) rejects floats / bools
+                acts = np.clip(acts, -1, 2)     # the cast below wraps mod 256: keep invalid values invalid (255 / 2)
+            np.copyto(views["action"], acts, casting="unsafe")
         stream = h["stream"]
         stream.wait_stream(t.cuda.current_stream(b["device"]))
         with t.cuda.stream(stream):
@@ -405,6 +458,7 @@ class RandomCartPoleVecEnv(RandomEnv):
             h["done"].copy_(b["done"], non_blocking=True)
             if self.track_truncated:
                 h["truncated"].copy_(b["truncated"], non_blocking=True)
+            h["counters"].copy_(self._violation_counter(b["device"]), non_blocking=True)    # 16 bytes: the error flags
             h["event"].record(stream)
 
     def host_bytes_per_step(self):
@@ -418,6 +472,9 @@ class RandomCartPoleVecEnv(RandomEnv):
         """Block until the last ``step_host_async`` finished -> (obs (N,4), reward, done, truncated) numpy views."""
         h = self._buffers["host"]
         h["event"].synchronize()
+        c = h["counters"]
+        if int(c[0]) | int(c[1]):          # the device flagged a gaussian failure or an invalid action (see ``step``)
+            self.check_dr_violations()
         v = h["np"]
         return v["obs"], v["reward"], v["done"], v["truncated"]
 
@@ -427,27 +484,50 @@ class RandomCartPoleVecEnv(RandomEnv):
         return self.step_host_wait()
 
     # ---- checkpoint / resume --------------------------------------------------------------------------
+    def _tensor_keys(self):
+        return ("state", "xi", "elapsed16" if self.lean else "elapsed", "episode", "beyond", "stats") + \
+               (("obs",) if self.noisy else ())
+
     def state_dict(self):
+        """Everything a resumed run needs to continue bit for bit: env buffers, the Philox key and step clock, the DR
+        sampler stream (seed_dr seed, call index), the loaded distribution and the dr_training flag."""
         b = self._alloc()
-        keys = ("state", "xi", "elapsed", "episode", "beyond", "stats") + (("obs",) if self.noisy else ())
-        out = {k: b[k].clone() for k in keys}
+        out = {k: b[k].clone() for k in self._tensor_keys()}     # the device->host free clone still orders after the kernels
         out.update(seed=self._seed, env_id0=self.env_id0, tick=self._tick, num_envs=self.num_envs,
-                   dtype=self._dtype_name)
+                   dtype=self._dtype_name, lean=self.lean,
+                   dr=dict(seed=self._dr_seed, calls=self._dr_calls, sampling=self.sampling, dr_training=self.dr_training,
+                           min_task=self.min_task.copy(), max_task=self.max_task.copy(), mean_task=self.mean_task.copy(),
+                           stdev_task=self.stdev_task.copy(),
+                           cov_task=np.copy(self.cov_task) if getattr(self, "cov_task", None) is not None else None))
+        self.check_dr_violations()          # synchronises; a checkpoint must not hide an error the reference raises
         return out
 
     def load_state_dict(self, sd):
-        if sd["num_envs"] != self.num_envs or sd["dtype"] != self._dtype_name:
-            raise ValueError("state_dict is for %d %s envs" % (sd["num_envs"], sd["dtype"]))
+        if sd["num_envs"] != self.num_envs or sd["dtype"] != self._dtype_name or sd.get("lean", False) != self.lean:
+            raise ValueError("state_dict is for %d %s envs%s" % (sd["num_envs"], sd["dtype"], " (lean)" if sd.get("lean") else ""))
         b = self._alloc()
-        for k in ("state", "xi", "elapsed", "episode", "beyond", "stats") + (("obs",) if self.noisy else ()):
+        for k in self._tensor_keys():
             b[k].copy_(sd[k])
         self._seed, self.env_id0, self._tick = sd["seed"], sd["env_id0"], sd["tick"]
+        dr = sd.get("dr")
+        if dr is not None:
+            self._dr_seed, self._dr_calls = dr["seed"], dr["calls"]
+            self.sampling, self.dr_training = dr["sampling"], dr["dr_training"]
+            self.min_task[:], self.max_task[:] = dr["min_task"], dr["max_task"]
+            self.mean_task[:], self.stdev_task[:] = dr["mean_task"], dr["stdev_task"]
+            if dr["cov_task"] is not None:
+                self.cov_task = np.copy(dr["cov_task"])
+            self._on_distribution_change()
         self._refresh_env_struct()
 
     # ---- introspection used by tests -------------------------------------------------------------------
     @property
     def elapsed(self):
-        return self._alloc()["elapsed"][:self.num_envs]
+        b = self._alloc()
+        if self.lean:
+            t = _device.torch()
+            return b["elapsed16"][:self.num_envs].to(t.int32) & 0xFFFF
+        return b["elapsed"][:self.num_envs]
 
     @property
     def episode(self):
@@ -465,4 +545,8 @@ class RandomCartPoleVecEnv(RandomEnv):
         b["state"][:, :self.num_envs].copy_(st.t())
         b["beyond"].fill_(-1)
         if elapsed is not None:
-            b["elapsed"][:self.num_envs].copy_(t.as_tensor(elapsed, device=b["device"]).to(t.int32))
+            el = t.as_tensor(elapsed, device=b["device"]).to(t.int32)
+            if self.lean:
+                b["elapsed16"][:self.num_envs].copy_(el.to(t.int16))
+            else:
+                b["elapsed"][:self.num_envs].copy_(el)

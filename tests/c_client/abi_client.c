@@ -41,15 +41,16 @@ int main(void)
     CK(cudaMalloc((void **)&d_state, 4 * LD * 8)); CK(cudaMalloc((void **)&d_xi, 4 * LD * 8));
     CK(cudaMalloc((void **)&d_reward, LD * 8)); CK(cudaMalloc((void **)&d_stats, 6 * 8));
     CK(cudaMalloc((void **)&d_elapsed, LD * 4)); CK(cudaMalloc((void **)&d_beyond, LD * 4));
-    CK(cudaMalloc((void **)&d_episode, LD * 4)); CK(cudaMalloc((void **)&d_viol, 8));
+    CK(cudaMalloc((void **)&d_episode, LD * 4)); CK(cudaMalloc((void **)&d_viol, 8 * RENV_NUM_COUNTERS));
     CK(cudaMalloc((void **)&d_action, LD)); CK(cudaMalloc((void **)&d_done, LD)); CK(cudaMalloc((void **)&d_trunc, LD));
     CK(cudaMemset(d_state, 0, 4 * LD * 8)); CK(cudaMemset(d_xi, 0, 4 * LD * 8)); CK(cudaMemset(d_elapsed, 0, LD * 4));
-    CK(cudaMemset(d_episode, 0, LD * 4)); CK(cudaMemset(d_beyond, 0xff, LD * 4)); CK(cudaMemset(d_viol, 0, 8));
+    CK(cudaMemset(d_episode, 0, LD * 4)); CK(cudaMemset(d_beyond, 0xff, LD * 4)); CK(cudaMemset(d_viol, 0, 8 * RENV_NUM_COUNTERS));
     cudaStream_t stream;
     CK(cudaStreamCreate(&stream));
 
     renv_cartpole_env env;
     env.state = d_state; env.xi = d_xi; env.elapsed = d_elapsed; env.episode = d_episode; env.beyond = d_beyond;
+    env.elapsed16 = NULL; env.progress = NULL;
     env.n = N; env.ld = LD; env.env_id0 = id0; env.seed = seed;
     renv_dr_cfg dr;
     memset(&dr, 0, sizeof dr);

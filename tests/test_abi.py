@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(lib, n), "%s declared in renv.h but not exported" % n
     assert sorted(_lib.SIGNATURES) == names, "ctypes binding and header disagree"
     header_version = int(re.search(r"#define RENV_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
-    assert _lib.load().renv_abi_version() == _lib.ABI_VERSION == header_version == 4
+    assert _lib.load().renv_abi_version() == _lib.ABI_VERSION == header_version == 5
 
 
 def test_header_constants_match_binding():
@@ -38,7 +38,7 @@ def test_header_constants_match_binding():
     assert int(re.search(r"#define RENV_MAX_DIM (\d+)", text).group(1)) == _lib.MAX_DIM
     assert int(re.search(r"#define RENV_NUM_STATS (\d+)", text).group(1)) == _lib.NUM_STATS
     assert ctypes.sizeof(_lib.DrCfg) == 8 + 3 * 8 * _lib.MAX_DIM + 8 * _lib.MAX_DIM ** 2
-    assert ctypes.sizeof(_lib.CartpoleEnv) == 5 * 8 + 4 * 8
+    assert ctypes.sizeof(_lib.CartpoleEnv) == 7 * 8 + 4 * 8
 
 
 def test_strerror_and_argument_validation_without_a_gpu():

@@ -38,11 +38,11 @@ def test_library_targets_sm_100a_only():
 
 
 def test_step_kernel_uses_128_bit_accesses_and_programmatic_dependent_launch(sass):
-    ops = _ops(_one(sass, "cartpole_step_kernelIfLb1ELb0"))        # <float, auto_reset, not noisy>: the hot kernel
+    ops = _ops(_one(sass, "cartpole_step_kernelIfLb1ELb0ELb0"))    # <float, auto_reset, not noisy, not lean>
     assert sum(o.startswith("LDG.E.128") for o in ops) >= 9        # 4 state rows + 4 xi rows + elapsed
     assert sum(o.startswith("STG.E.128") for o in ops) >= 6        # 4 state rows + elapsed + reward
     assert "ACQBULK" in ops and "PREEXIT" in ops                   # griddepcontrol.wait / launch_dependents
-    ops64 = _ops(_one(sass, "cartpole_step_kernelIdLb1ELb0"))
+    ops64 = _ops(_one(sass, "cartpole_step_kernelIdLb1ELb0ELb0"))
     assert sum(o.startswith("LDG.E.128") for o in ops64) >= 10 and any(o.startswith("DFMA") for o in ops64)
 
 
