@@ -5,11 +5,15 @@
     python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference's CPU path (oracle port)
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     # N > 1: one rank per GPU
 
-One "step" = one pass of the single-step kernel (RandomCartPoleEnv.step + TimeLimit + auto-reset + uniform
-DR resample on reset) over one batch of 2^20 envs -- BASELINE.json configs[1].  Per rank, 4 independent
-batches (248 MB > 126 MB L2) are stepped round-robin so every launch streams its working set from HBM.
-The K timed steps are captured once in a CUDA graph and replayed (a 10 us kernel is otherwise bound by
-the Python/ctypes launch path); the eager public-API rate is reported beside it as `value_eager`.
+One "step" = one pass of the single-step kernel (RandomCartPoleEnv.step + TimeLimit + auto-reset + uniform DR
+resample on reset) over one batch of 2^20 envs -- BASELINE.json configs[1].  Per rank, 4 independent batches
+(248 MB > 126 MB L2) are stepped round-robin so every launch streams its working set from HBM.  The K steps are
+captured once in a CUDA graph (a 10 us kernel is otherwise bound by the Python/ctypes launch path) and the graph is
+replayed >= 200 times (>= 50 ms of timed region) with a CUDA event after every replay: `ms_per_step` is the median
+replay / K, the spread is reported beside it, and the eager public-API rate is reported as `value_eager`.
+
+The reference arm (`--impl reference`) runs the REFERENCE's own RandomCartPoleEnv objects (oracle/_ref, see
+oracle/make_ref.py; the bit-exact port only if those copies are absent) on all host cores for >= 2 s whatever --steps is.
 
 Rank 0 prints ONE JSON line (see the keys at the bottom of main()).
 """
@@ -43,6 +47,9 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="skip the size sweep / rollout / sampler extras")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--ref-seconds", type=float, default=4.0, help="wall time of the reference arm's timed region")
+    ap.add_argument("--min-replays", type=int, default=200)
+    ap.add_argument("--min-region-ms", type=float, default=50.0)
     return ap.parse_args()
 
 
@@ -60,21 +67,28 @@ def workload_config(args, world):
 
 # --------------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path, all host cores, same metric."""
+    """Reference arm: the reference's own CPU implementation of the path, all host cores, same metric and config.
+
+    A "step" of this arm is a BLOCK of gym-0.21 SyncVectorEnv steps over procs x 64 scalar envs: the driver's
+    `--steps 20` would otherwise time 7 ms.  Every worker steps its envs for max(2 s, ...) of wall time; the value is
+    env-steps / the slowest worker's time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import cpu_bench
     procs = os.cpu_count() or 1
     envs_per_proc = 64
-    res = cpu_bench.run(procs, envs_per_proc, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    seconds = max(2.0, args.ref_seconds)
+    res = cpu_bench.run(procs, envs_per_proc, steps=0, warmup=max(20, args.warmup), seconds=seconds)
+    k = max(1, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / max(1, args.steps),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / k,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args, 1), reference_step="one gym-0.21 SyncVectorEnv.step over %d procs x %d "
-                           "scalar envs (bounded sample of the same workload)" % (procs, envs_per_proc)),
-            "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": procs, "kind": "port",
-                             "sample": res["sample"], "cpu_model": res["cpu_model"]},
+            "config": workload_config(args, max(1, args.gpus)),
+            "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": procs, "kind": res["kind"],
+                             "sample": res["sample"], "cpu_model": res["cpu_model"], "seconds": res["seconds"],
+                             "step": "one of the %d timed steps = %.0f gym-0.21 SyncVectorEnv.step calls over %d procs x %d "
+                                     "reference RandomCartPoleEnv objects" % (k, res["steps"] / k, procs, envs_per_proc)},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -166,7 +180,7 @@ def run_b200(args):
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
-    cpu_baseline = None
+    cpu_baseline, cpu_c1 = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process; worker processes are forked inside the child
         out = subprocess.run([sys.executable, "-m", "oracle.cpu_bench", "--seconds", str(args.cpu_seconds)], cwd=ROOT,
@@ -177,6 +191,10 @@ def run_b200(args):
                             "sample": r["sample"], "cpu_model": r["cpu_model"], "seconds": r["seconds"]}
         else:
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: " + out.stderr[-200:]}
+        # BASELINE.json configs[0] / BASELINE.md "C1": the reference's own single-env demo loop on one host core
+        out = subprocess.run([sys.executable, "-m", "oracle.cpu_bench", "--c1"], cwd=ROOT, stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, text=True)
+        cpu_c1 = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"failed": out.stderr[-200:]}
 
     import torch
     import torch.distributed as dist
@@ -209,37 +227,35 @@ def run_b200(args):
         return max_over_ranks(e0.elapsed_time(e1))
 
     n, R, A = args.envs, args.batches, 8
-    envs, actions = [], []
-    for b in range(R):
-        env = renv.RandomCartPoleVecEnv(n, dtype=args.dtype, device=dev, seed=0, env_id0=(rank * R + b) * n,
-                                        track_truncated=False, track_episodes=False)
-        env.set_dr_distribution("uniform", SEARCH)
-        env.set_dr_training(True)
-        env.reset()
-        acts = []
-        for k in range(A):
-            a = torch.empty(n, dtype=torch.uint8, device=dev)
-            _lib.call("renv_random_actions_u8", _device.ptr(a), n, env.env_id0, 0, k, _device.stream_ptr(dev))
-            acts.append(a)
-        envs.append(env); actions.append(acts)
-    torch.cuda.synchronize()
-
-    def step_i(i):
-        b = i % R
-        envs[b].step(actions[b][(i // R) % A])
-
-    for i in range(args.warmup):
-        step_i(i)
-    torch.cuda.synchronize()
-
-    # eager public-API loop (Python + ctypes per launch)
     K = args.steps
-    ms_eager = timed(lambda: [step_i(i) for i in range(K)])
 
-    # the same K steps as one CUDA graph.  `chain`: one stream, launches strictly serialised.  `branches`: the R
+    def make_batches(tile_ordering):
+        envs, actions = [], []
+        for b in range(R):
+            env = renv.RandomCartPoleVecEnv(n, dtype=args.dtype, device=dev, seed=0, env_id0=(rank * R + b) * n,
+                                            track_truncated=False, track_episodes=False, tile_ordering=tile_ordering)
+            env.set_dr_distribution("uniform", SEARCH)
+            env.set_dr_training(True)
+            env.reset()
+            acts = []
+            for k in range(A):
+                a = torch.empty(n, dtype=torch.uint8, device=dev)
+                _lib.call("renv_random_actions_u8", _device.ptr(a), n, env.env_id0, 0, k, _device.stream_ptr(dev))
+                acts.append(a)
+            envs.append(env); actions.append(acts)
+        torch.cuda.synchronize()
+        return envs, actions
+
+    def stepper(envs, actions):
+        def step_i(i):
+            b = i % R
+            envs[b].step(actions[b][(i // R) % A])
+        return step_i
+
+    # the same K steps as one CUDA graph.  `chain`: one stream, launches in stream order.  `branches`: the R
     # independent env batches on R parallel graph branches, so one batch's tail wave overlaps another's head
     # (a 2^20-env launch is only 1.7 waves of CTAs).
-    def capture(parallel):
+    def capture(step_i, parallel):
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -262,38 +278,103 @@ def run_b200(args):
         torch.cuda.synchronize()
         return g
 
-    reps = 3
-    chain = capture(False)
-    ms_chain = sorted(timed(chain.replay) for _ in range(reps))[reps // 2]
-    graph = capture(True)
+    def time_replays(graph, replays):
+        """`replays` back-to-back replays of a K-step graph with a CUDA event after each one (an event record does not
+        serialise anything): returns per-replay milliseconds (max over ranks of each percentile is taken by the caller)
+        and the whole region."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(replays + 1)]
+        barrier(); torch.cuda.synchronize()
+        ev[0].record()
+        for r in range(replays):
+            graph.replay()
+            ev[r + 1].record()
+        torch.cuda.synchronize(); barrier()
+        per = sorted(ev[r].elapsed_time(ev[r + 1]) for r in range(replays))
+        return per, ev[0].elapsed_time(ev[-1])
+
+    def pct(per, q):
+        return per[min(len(per) - 1, int(q * len(per)))]
+
+    bytes_per = BYTES_PER_STEP[args.dtype]
+    est_ms = K * n * bytes_per / 5.5e12 * 1e3                       # a first guess of one replay
+    replays = int(max(args.min_replays, -(-args.min_region_ms // est_ms)))
+
+    # ---- (1) the public API as a user drives it: default env (tile-granular step ordering at this size), ONE stream
+    envs_t, actions_t = make_batches("auto")
+    step_t = stepper(envs_t, actions_t)
+    for i in range(max(args.warmup, 3)):
+        step_t(i)
+    torch.cuda.synchronize()
+    k_eager = max(K, 400)
+    ms_eager = timed(lambda: [step_t(i) for i in range(k_eager)])
+    chain = capture(step_t, False)
+    per_chain, _ = time_replays(chain, replays)
+    ms_chain = max_over_ranks(pct(per_chain, 0.5))
+    del chain
+
+    # ---- (2) the headline: grid-ordered launches, the R independent batches on R parallel graph branches
+    envs, actions = make_batches(False)
+    step_g = stepper(envs, actions)
+    for i in range(max(args.warmup, 3)):
+        step_g(i)
+    torch.cuda.synchronize()
+    chain_g = capture(step_g, False)
+    per_chain_g, _ = time_replays(chain_g, replays)
+    ms_chain_g = max_over_ranks(pct(per_chain_g, 0.5))
+    del chain_g
+    graph = capture(step_g, True)
 
     clocks = ClockSampler(local_rank).start() if rank == 0 else None
     t_wall0 = time.time()
-    ms_runs = [timed(graph.replay) for _ in range(reps)]
+    per, region_ms = time_replays(graph, replays)
     # keep the GPU under the same load for >= 0.5 s so that nvidia-smi gets samples of the timed workload
     while time.time() - t_wall0 < 0.6:
         graph.replay()
     torch.cuda.synchronize()
     t_wall1 = time.time()
     clock_info = clocks.stop(t_wall0, t_wall1) if clocks else None
-    ms = sorted(ms_runs)[len(ms_runs) // 2]         # median of 3 replays of the K-step graph
+    ms = max_over_ranks(pct(per, 0.5))              # median replay of the K-step graph
+    region_ms = max_over_ranks(region_ms)
+    spread = {"replays": replays, "region_ms": region_ms, "p05_us_per_step": 1e3 * max_over_ranks(pct(per, 0.05)) / K,
+              "p50_us_per_step": 1e3 * ms / K, "p95_us_per_step": 1e3 * max_over_ranks(pct(per, 0.95)) / K,
+              "mean_us_per_step": 1e3 * region_ms / (replays * K)}
     value = world * n * K / (ms * 1e-3)
-    value_eager = world * n * K / (ms_eager * 1e-3)
+    value_eager = world * n * k_eager / (ms_eager * 1e-3)
+
+    # one launch in isolation (sync on both sides, the 4 batches rotating so that it streams from HBM): the number an
+    # ncu launch list shows; the amortised figures above overlap consecutive launches
+    iso = []
+    for i in range(40):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        torch.cuda._sleep(400000)       # ~200 us of busy stream: the launch below is queued before the GPU gets to it,
+        e0.record(); step_g(i); e1.record()     # so the events bracket the kernel and not the host's launch latency
+        torch.cuda.synchronize()
+        iso.append(e0.elapsed_time(e1))
+    iso_us = 1e3 * max_over_ranks(sorted(iso)[len(iso) // 2])
 
     peak, peak_src = measured_peaks()
     per_launch_ms = ms / K
-    achieved = BYTES_PER_STEP[args.dtype] * n / (per_launch_ms * 1e-3) / 1e9
+    achieved = bytes_per * n / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "cartpole_step_kernel<%s>" % ("float" if args.dtype == "float32" else "double"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "bytes_per_env_step": BYTES_PER_STEP[args.dtype], "launch_us": per_launch_ms * 1e3,
+                "bytes_per_env_step": bytes_per, "launch_us": per_launch_ms * 1e3, "isolated_launch_us": iso_us,
+                "launch_us_note": "launch_us = median graph replay / K with consecutive launches overlapping (amortised); "
+                                  "isolated_launch_us = one launch alone on the GPU, nothing before or after it to overlap "
+                                  "with (event-timed behind a spin kernel, so without the host's launch latency)",
                 "traffic": ncu_traffic(args.dtype)}
+
+    def roof(ms_k):
+        gbs = bytes_per * n / (ms_k / K * 1e-3) / 1e9
+        return {"launch_us": 1e3 * ms_k / K, "achieved": gbs, "frac": gbs / peak}
 
     # ---- end to end through the public host-buffer API: pinned H2D actions, D2H obs/reward/done every step.
     # The R env batches are stepped round-robin with one step in flight per batch (step_host_async / _wait), so
     # batch b's device->host transfer overlaps batch b+1's host->device transfer and kernel.
     import numpy as np
-    k_e2e = max(2 * R, min(K, 200))
+    k_e2e = max(2 * R, min(max(K, 100), 200))
     host_actions = [a.cpu().numpy() for a in actions[0][:2]]
+    del envs_t, actions_t
     torch.cuda.synchronize()
 
     def e2e_loop(steps):
@@ -312,8 +393,13 @@ def run_b200(args):
     t0 = time.perf_counter(); e2e_loop(k_e2e); torch.cuda.synchronize(); t1 = time.perf_counter()
     ms_e2e = max_over_ranks((t1 - t0) * 1e3)
     h2d_bytes, d2h_bytes = envs[0].host_bytes_per_step()     # counted from the tensors the call copies
-    e2e = {"value": world * n * k_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+    e2e_value = world * n * k_e2e / (ms_e2e * 1e-3)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
            "d2h_bytes_per_step": d2h_bytes, "steps": k_e2e, "ms_per_step": ms_e2e / k_e2e,
+           "bound": "pcie (device->host copies of obs + done: %.1f GB/s per GPU, %.1f GB/s over the box; a Gen5 x16 link "
+                    "gives ~55 GB/s and the host side of this box ~118 GB/s in total with 8 GPUs copying at once, "
+                    "profiles/r1/pcie_aggregate_8gpu.txt)" % (e2e_value / world * d2h_bytes / n / 1e9,
+                                                             e2e_value * d2h_bytes / n / 1e9),
            "api": "RandomCartPoleVecEnv.step_host_async(numpy uint8 actions) / step_host_wait() -> numpy obs, reward, "
                   "done; %d env batches round-robin, one step in flight per batch; obs + done cross PCIe, the reward "
                   "(identically 1.0 under auto-reset, random_cartpole.py:207-212) is a constant host array" % R}
@@ -321,6 +407,8 @@ def run_b200(args):
     extras = {}
     if not args.no_extras:
         extras = run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, peak)
+        if cpu_c1 is not None:
+            extras["cfg1_cpu_reference_single_env"] = cpu_c1
 
     if world > 1:
         dist.destroy_process_group()
@@ -329,13 +417,17 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e, "gpu_launches": K,
+            "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e, "gpu_launches": K * replays,
             "launch_mode": "one CUDA graph of K cartpole_step_kernel launches, the %d independent env batches on %d "
-                           "parallel graph branches; launch_us = timed region / K; median of %d replays" % (R, R, reps),
+                           "parallel graph branches (grid-ordered launches); the graph is replayed %d times back to back "
+                           "(%.0f ms), ms_per_step = median replay / K" % (R, R, replays, region_ms),
+            "timing": spread,
             "value_eager": value_eager, "value_graph_single_chain": world * n * K / (ms_chain * 1e-3),
-            "roofline_single_chain": {"launch_us": 1e3 * ms_chain / K,
-                                      "achieved": BYTES_PER_STEP[args.dtype] * n / (ms_chain / K * 1e-3) / 1e9,
-                                      "frac": BYTES_PER_STEP[args.dtype] * n / (ms_chain / K * 1e-3) / 1e9 / peak},
+            "single_stream": {"note": "the default env (tile-granular step ordering, include/renv.h progress) on ONE "
+                                      "stream: what a plain step() loop over %d env batches gets" % R,
+                              "eager_python_loop": roof(ms_eager * K / k_eager), "graph_chain": roof(ms_chain),
+                              "graph_chain_grid_ordered": roof(ms_chain_g)},
+            "roofline_single_chain": roof(ms_chain),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -380,6 +472,64 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
     del env, a
     torch.cuda.empty_cache()
 
+    # Lean step (renv_cartpole_step_lean_f32): uint16 TimeLimit counter, no reward store: 35 B read + 19 B written = 54 B
+    # per env-step; state / done bit-identical to the 62-byte step (tests/test_gpu_step_modes.py).  4 x 2^20 envs
+    # round-robin on one stream (default tile-granular ordering) and 2^24 envs.
+    n = 1 << 20
+    lean = []
+    for b in range(4):
+        e = renv.RandomCartPoleVecEnv(n, dtype="float32", device=dev, seed=1, env_id0=(rank * 4 + b) * n,
+                                      track_truncated=False, track_episodes=False, lean=True)
+        e.set_dr_distribution("uniform", SEARCH); e.set_dr_training(True); e.reset()
+        lean.append(e)
+    a = lean[0].sample_actions().clone()
+    for i in range(40):
+        lean[i % 4].step(a)
+    ms = timed(lambda: [lean[i % 4].step(a) for i in range(800)])
+    gbs = 54 * n * 800 / (ms * 1e-3) / 1e9
+    out["step_lean_f32_1M_x4_one_stream"] = {"env_steps_per_s": agg(n * 800, ms), "launch_us": 1e3 * ms / 800, "gbs_per_gpu": gbs,
+                                             "frac_of_hbm_peak": gbs / peak, "bytes_per_env_step": 54,
+                                             "traffic": (json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                                                         .get("cartpole_step_lean_float32_1M"))}
+    del lean, a
+    torch.cuda.empty_cache()
+    n = 1 << 24
+    e = renv.RandomCartPoleVecEnv(n, dtype="float32", device=dev, seed=1, env_id0=rank * n, track_truncated=False,
+                                  track_episodes=False, lean=True)
+    e.set_dr_distribution("uniform", SEARCH); e.set_dr_training(True); e.reset()
+    a = e.sample_actions().clone()
+    for _ in range(3):
+        e.step(a)
+    ms = timed(lambda: [e.step(a) for _ in range(40)])
+    gbs = 54 * n * 40 / (ms * 1e-3) / 1e9
+    out["step_lean_f32_16M"] = {"env_steps_per_s": agg(n * 40, ms), "launch_us": 1e3 * ms / 40, "gbs_per_gpu": gbs,
+                                "frac_of_hbm_peak": gbs / peak, "bytes_per_env_step": 54, "envs_per_gpu": n}
+    del e, a
+    torch.cuda.empty_cache()
+
+    # BASELINE.json configs[0] through the drop-in gym env (one env, one launch per step): the scalar API's latency
+    if rank == 0:
+        genv = renv.gym.make("RandomCartPole-v0")
+        genv.set_dr_distribution("uniform", SEARCH); genv.set_dr_training(True)
+        genv.seed(0); genv.action_space.seed(0)
+        genv.reset()
+        for _ in range(200):
+            _, _, d, _ = genv.step(genv.action_space.sample())
+            if d:
+                genv.reset()
+        t0 = time.perf_counter()
+        steps_c1, episodes = 10000, 0
+        for _ in range(steps_c1):
+            _, _, d, _ = genv.step(genv.action_space.sample())
+            if d:
+                genv.reset(); episodes += 1
+        dt = time.perf_counter() - t0
+        out["cfg1_gpu_dropin_single_env"] = {"env_steps_per_s": steps_c1 / dt, "us_per_step": 1e6 * dt / steps_c1,
+                                             "episodes": episodes, "mean_episode_length": steps_c1 / max(1, episodes),
+                                             "api": "gym.make('RandomCartPole-v0').step(a): the test_random_policy.py loop, "
+                                                    "10000 steps incl. resets with uniform DR resample"}
+        genv.close()
+
     # Noisy variant: +16 B/env-step for the separate obs rows, one Philox block + Box-Muller per env
     n = 1 << 24
     env = renv.RandomCartPoleVecEnv(n, dtype="float32", device=dev, seed=1, env_id0=rank * n, track_truncated=False,
@@ -395,17 +545,28 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
     del env, a
     torch.cuda.empty_cache()
 
-    # FP32 / FP64 FMA peaks for the rollout roofline
+    # FP32 / FP64 FMA peaks for the rollout roofline and the Philox issue roof of the samplers (micro-benchmarks that
+    # live outside the product library: profiles/microbench/)
     sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    mb = ctypes.CDLL(os.path.join(ROOT, "profiles", "microbench", "librenv_microbench.so"))
     peaks = {}
     for suffix, dt, iters in (("f32", torch.float32, 20000), ("f64", torch.float64, 10000)):
         blocks, threads = sm * 8, 256
         buf = torch.empty(blocks * threads, dtype=dt, device=dev)
-        launch = lambda: _lib.call("renv_fma_peak_" + suffix, _device.ptr(buf), blocks, threads, iters, _device.stream_ptr(dev))  # noqa: E731
-        launch(); torch.cuda.synchronize()
+        fn = getattr(mb, "renv_fma_peak_" + suffix)
+        launch = lambda: fn(ctypes.c_void_p(buf.data_ptr()), blocks, threads, iters, _device.stream_ptr(dev))  # noqa: E731
+        assert launch() == 0; torch.cuda.synchronize()
         ms = timed(launch)
         peaks[suffix] = 2.0 * blocks * threads * 8 * iters / (ms * 1e-3) / 1e12
     out["fma_peak_tflops"] = peaks
+    blocks, threads, iters = sm * 8, 256, 2000
+    buf = torch.empty(blocks * threads * 4, dtype=torch.int32, device=dev)
+    launch = lambda: mb.renv_philox_peak(ctypes.c_void_p(buf.data_ptr()), blocks, threads, iters, ctypes.c_uint64(1), _device.stream_ptr(dev))  # noqa: E731
+    assert launch() == 0; torch.cuda.synchronize()
+    ms = timed(launch)
+    philox_blocks_per_s = blocks * threads * iters / (ms * 1e-3)
+    out["philox_peak"] = {"blocks_per_s": philox_blocks_per_s, "fp32_output_gbs": philox_blocks_per_s * 16 / 1e9,
+                          "note": "Philox4x32-10 with nothing else in the loop: the int-multiply issue roof of the samplers"}
 
     # BASELINE configs[3]: fused 500-step rollout, 2^24 envs per GPU, linear policy, + the stats all-gather
     # (w = None: the random policy of BASELINE configs[0] / test_random_policy.py, one Philox block per env-step)
@@ -468,8 +629,12 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
         s.sample_tasks_tensor(n, out=buf); torch.cuda.synchronize()
         ms = timed(lambda: [s.sample_tasks_tensor(n, out=buf) for _ in range(3)]) / 3
         gbs = n * 30 * 4 / (ms * 1e-3) / 1e9
+        # every 30-dim sample costs 8 Philox blocks (7.5 rounded up), i.e. 128 B of raw draws for 120 B written
+        philox_gbs = out["philox_peak"]["fp32_output_gbs"] * 30.0 / 32.0
         out["sampler_f32_humanoid30_" + dr_type] = {"xi_per_s": agg(n, ms), "ms": ms, "gbs_per_gpu": gbs,
-                                                    "frac_of_hbm_peak": gbs / peak}
+                                                    "frac_of_hbm_peak": gbs / peak,
+                                                    "bound": "tensor + philox" if dr_type == "fullgaussian" else "philox int-mul issue",
+                                                    "frac_of_philox_roof": gbs / philox_gbs}
         del buf
     torch.cuda.empty_cache()
     return out

@@ -1,9 +1,12 @@
 """Load the UNMODIFIED reference hot-path source by file path.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  Works only where
-``/root/reference`` is mounted (the build container).  The GPU box has no
-reference tree: tests that need this module skip there and rely on the golden
-vectors this loader produced (``oracle/make_golden.py`` -> ``tests/golden/``).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The source comes from
+``/root/reference`` where that is mounted (the build container) and otherwise
+from ``oracle/_ref/`` -- byte-identical copies of the two files made there by
+``oracle/make_ref.py`` (git-ignored, shipped to the GPU box with the snapshot)
+so that ``bench.py``'s CPU legs can time the real reference on the box's host.
+Tests that compare against the live reference skip when neither is present and
+rely on the golden vectors this loader produced (``oracle/make_golden.py``).
 
 Why by path: ``import random_envs`` runs ``random_envs/__init__.py:1`` which
 imports the MuJoCo sub-package (``jinja/jinja_mujoco_env.py:15-18`` raises
@@ -24,11 +27,25 @@ import numpy as np
 
 from . import gym_shim
 
-REFERENCE_ROOT = os.environ.get("RENV_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _has_sources(root):
+    return all(os.path.isfile(os.path.join(root, "random_envs", f)) for f in ("random_env.py", "random_cartpole.py"))
+
+
+def _resolve_root():
+    for cand in (os.environ.get("RENV_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and _has_sources(cand):
+            return cand
+    return os.environ.get("RENV_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "random_envs", "random_cartpole.py"))
+    return _has_sources(REFERENCE_ROOT)
 
 
 _cache = {}

@@ -243,9 +243,11 @@ class RandomCartPoleVecEnv(RandomEnv):
         src = actions if isinstance(actions, t.Tensor) else t.as_tensor(np.asarray(actions))
         if tuple(src.shape) != (n,):
             raise ValueError("actions must have shape (%d,), got %s" % (n, tuple(src.shape)))
-        if src.dtype.is_floating_point or src.dtype == t.bool:
-            raise AssertionError("%r (%s) invalid" % (actions, type(actions)))   # Discrete(2) rejects floats and bools
-        if src.dtype != t.uint8:
+        if src.dtype.is_floating_point:
+            raise AssertionError("%r (%s) invalid" % (actions, type(actions)))   # Discrete(2) rejects floats
+        if src.dtype == t.bool:         # a comparison result, e.g. (obs[:, 2] > 0): 0 / 1 by construction
+            src = src.to(t.uint8)
+        elif src.dtype != t.uint8:
             # a wider integer would be truncated to 8 bits by the staging copy: clamp so that anything outside
             # {0, 1} stays outside (negative -> 255, large -> 255) and is caught on the device
             src = src.to(b["device"], non_blocking=True)
@@ -465,7 +467,8 @@ class RandomCartPoleVecEnv(RandomEnv):
         """(host->device, device->host) bytes one ``step_host`` moves over PCIe."""
         esize = 4 if self._dtype_name == "float32" else 8
         ld = self._alloc()["ld"]
-        d2h = 4 * ld * esize + ld + (0 if self.auto_reset else ld * esize) + (ld if self.track_truncated else 0)
+        d2h = 4 * ld * esize + ld + (0 if self.auto_reset else ld * esize) + (ld if self.track_truncated else 0) \
+            + 8 * _lib.NUM_COUNTERS
         return ld, d2h
 
     def step_host_wait(self):
