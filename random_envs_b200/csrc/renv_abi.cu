@@ -114,6 +114,21 @@ int launch_pdl(void (*kernel)(const Args), unsigned blocks, unsigned threads, cu
     return rc != cudaSuccess ? (int)rc : launch_status();
 }
 
+// fp32: the packed-transform kernel; fp64: the generic one
+template <int kType, int kStore>
+void launch_sampler(float *out, int64_t n, const DrCfgPrepared<float> &c, uint64_t seed, uint64_t sample_id0, uint32_t call,
+                    unsigned long long *violations, int items, unsigned blocks, cudaStream_t st)
+{
+    const PhiloxKeys ks = philox_keys((uint32_t)seed, (uint32_t)(seed >> 32));
+    dr_sample_f32_kernel<kType, kStore><<<blocks, kSampleThreads, 0, st>>>(out, n, c, seed, ks, sample_id0, call, violations, items);
+}
+template <int kType, int kStore>
+void launch_sampler(double *out, int64_t n, const DrCfgPrepared<double> &c, uint64_t seed, uint64_t sample_id0, uint32_t call,
+                    unsigned long long *violations, int items, unsigned blocks, cudaStream_t st)
+{
+    dr_sample_kernel<double, kType, kStore><<<blocks, kSampleThreads, 0, st>>>(out, n, c, seed, sample_id0, call, violations, items);
+}
+
 template <typename T>
 int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0, uint32_t call,
               unsigned long long *violations, void *stream)
@@ -166,8 +181,7 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
     constexpr int P = Pack<T>::kPerBlock;
     const int store = cfg->dim % P == 0 ? 0 : (sizeof(T) == 4 && cfg->dim % 2 == 0 ? 1 : 2);
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define RENV_LAUNCH_SAMPLER(TYPE, STORE) \
-    dr_sample_kernel<T, TYPE, STORE><<<(unsigned)blocks, kSampleThreads, 0, st>>>(out, n, c, seed, sample_id0, call, violations, items)
+#define RENV_LAUNCH_SAMPLER(TYPE, STORE) launch_sampler<TYPE, STORE>(out, n, c, seed, sample_id0, call, violations, items, (unsigned)blocks, st)
 #define RENV_LAUNCH_SAMPLER_TYPE(TYPE) \
     do { if (store == 0) RENV_LAUNCH_SAMPLER(TYPE, 0); else if (store == 1) RENV_LAUNCH_SAMPLER(TYPE, 1); \
          else RENV_LAUNCH_SAMPLER(TYPE, 2); } while (0)

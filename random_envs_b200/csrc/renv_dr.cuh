@@ -16,6 +16,7 @@
 //         Both transforms start from the integer draw (r >> 8): the 2^-24 scale is folded into their first FMA.
 #pragma once
 #include "renv_philox.cuh"
+#include "renv_pack.cuh"
 
 namespace renv {
 
@@ -249,6 +250,80 @@ __device__ __forceinline__ unsigned sample_dim_block(const Cfg &cfg, uint64_t se
                                                      uint32_t purpose, int j, T *out)
 {
     return sample_dim_block<T>(cfg.dr_type, load_dim_block(cfg, j), seed, id, tick, purpose, j, out);
+}
+
+// ---- fp32 sampler hot path: the transforms of one Philox block on PACKED pairs (FFMA2 / FMUL2) ------------------
+// Same operations, operands and rounding as the scalar Num<float> / Pack<float> code above, lane for lane (a packed
+// lane rounds like the scalar instruction; -x is produced by a second FMA with negated constants, which is exact
+// because rounding is sign-symmetric) -- so the values are bit-identical -- in half the FMA-pipe issue slots.
+struct DimBlockPacked {
+    u64 a01, a23, b01, b23;         // uniform: off / scale * 2^-24;  truncnorm, gaussian: mean / std
+    float floor[4];
+    unsigned valid;
+};
+__device__ __forceinline__ DimBlockPacked pack_dim_block(const DimBlock<float> &b)
+{
+    DimBlockPacked p;
+    p.a01 = pk(b.a[0], b.a[1]); p.a23 = pk(b.a[2], b.a[3]);
+    p.b01 = pk(b.b[0], b.b[1]); p.b23 = pk(b.b[2], b.b[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p.floor[k] = b.floor[k];
+    p.valid = b.valid;
+    return p;
+}
+__device__ __forceinline__ u64 bits24_pair(uint32_t ra, uint32_t rb) { return pk((float)(ra >> 8), (float)(rb >> 8)); }
+
+// Pack<float>::uniform_affine
+__device__ __forceinline__ void uniform4_packed(uint4 r, const DimBlockPacked &p, float out[4])
+{
+    unpk(fma2(p.b01, bits24_pair(r.x, r.y), p.a01), out[0], out[1]);
+    unpk(fma2(p.b23, bits24_pair(r.z, r.w), p.a23), out[2], out[3]);
+}
+// Num<float>::tn_z_bits for two draws, then the affine map mean + std * z
+__device__ __forceinline__ u64 truncnorm_pair(uint32_t ra, uint32_t rb, u64 std2, u64 mean2)
+{
+    const float X = (float)kPhiSpan;
+    const u64 F = bits24_pair(ra, rb);
+    const u64 x = fma2(F, splat(2.0f * X / 16777216.0f), splat(-X));
+    const u64 nx = fma2(F, splat(-2.0f * X / 16777216.0f), splat(X));          // == -x exactly
+    float w0, w1;
+    unpk(fma2(nx, x, splat(1.0f)), w0, w1);
+    const u64 t = fma2(pk(lg2_approx(w0), lg2_approx(w1)), splat(-0.69314718056f), splat(-1.25f));
+    u64 g = splat(-6.496782899e-06f);
+    g = fma2(g, t, splat(4.291892561e-05f));
+    g = fma2(g, t, splat(2.023686373e-04f));
+    g = fma2(g, t, splat(-3.186480695e-03f));
+    g = fma2(g, t, splat(3.552299202e-03f));
+    g = fma2(g, t, splat(3.528738932e-01f));
+    g = fma2(g, t, splat(1.682294103e+00f));
+    return fma2(std2, mul2(g, x), mean2);
+}
+// Num<float>::normal_pair for one (radius, angle) draw pair, then the affine map
+__device__ __forceinline__ u64 gaussian_pair(uint32_t ra, uint32_t rb, u64 std2, u64 mean2)
+{
+    const float two_ln2 = 1.3862943611198906f, two_pi = 6.283185307179586f;
+    const float rad = sqrt_approx(fmaf(lg2_approx((float)((ra >> 8) + 1u)), -two_ln2, 24.0f * two_ln2));
+    const float ang = fmaf((float)(rb >> 8), two_pi / 16777216.0f, -0.5f * two_pi);
+    return fma2(std2, mul2(splat(rad), pk(__cosf(ang), __sinf(ang))), mean2);
+}
+// Attempt 0 for a whole block.  Returns true when some valid dim fell below its floor (the caller then takes the
+// scalar first_attempt / redraws path for this block: the reference's retry loop, random_env.py:158-171,177-190).
+template <int kDrType>
+__device__ __forceinline__ bool first_attempt_packed(uint4 r, const DimBlockPacked &p, float out[4])
+{
+    if (kDrType == kDrUniform) {
+        uniform4_packed(r, p, out);
+        return false;
+    }
+    if (kDrType == kDrTruncnorm) {
+        unpk(truncnorm_pair(r.x, r.y, p.b01, p.a01), out[0], out[1]);
+        unpk(truncnorm_pair(r.z, r.w, p.b23, p.a23), out[2], out[3]);
+    } else {
+        unpk(gaussian_pair(r.x, r.y, p.b01, p.a01), out[0], out[1]);
+        unpk(gaussian_pair(r.z, r.w, p.b23, p.a23), out[2], out[3]);
+    }
+    // dims beyond `dim` have mean = std = floor = 0: 0 < 0 is false, no mask needed
+    return out[0] < p.floor[0] || out[1] < p.floor[1] || out[2] < p.floor[2] || out[3] < p.floor[3];
 }
 
 }  // namespace renv

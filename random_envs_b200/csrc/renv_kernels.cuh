@@ -732,6 +732,87 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
     if (kDrType == kDrGaussian && viol && violations) atomicAdd(violations, (unsigned long long)viol);
 }
 
+// The fp32 specialisation of the loop above (the throughput path; the generic kernel stays for fp64 and is what
+// this one was derived from -- same work decomposition, same draws, bit-identical output).  The sampler is bound by
+// instruction ISSUE, not by HBM (ncu, round 1: ALU pipe 59 %, stalls math-throttle / not-selected / dispatch; Philox
+// alone is 20 IMAD.WIDE + 20 LOP3 per 16 output bytes and tops out at 6.8 TB/s), so every instruction removed from
+// the per-block loop is throughput:
+//   * the Philox counter of a thread's k-th sample differs from its first only in word 0 (the low half of the
+//     sample id) as long as the id does not cross a multiple of 2^32, so the loop runs in (at most two) segments with
+//     words 1..3 constant: the first round's M1 * c.z and all its XORs with constants, and the second round's
+//     M0 * c'.x, are hoisted by the compiler -- 37 instead of 40 Philox instructions and no 64-bit id arithmetic;
+//   * the output pointer is advanced instead of re-derived from a 32-bit offset (2 instead of 4 instructions);
+//   * the transforms run on packed pairs (renv_dr.cuh: FFMA2 / FMUL2, the same rounding lane for lane);
+//   * attempt 0 only answers "did any dim fall below its floor" (4 FSETP); the retry loop of the reference, with
+//     its per-dim bookkeeping, is out of line.
+#ifndef RENV_SAMPLER_F32_CTAS
+#define RENV_SAMPLER_F32_CTAS 3
+#endif
+// The reference's retry loop for one block whose first attempt left some dim below its floor (random_env.py:158-171,
+// 177-190): out of line, so that the per-block loop of the kernel stays Philox + packed transform + store.
+struct RedoneBlock { float v0, v1, v2, v3; unsigned viol; };      // returned in registers: no stack traffic in the loop
+template <int kDrType>
+__device__ __noinline__ RedoneBlock sampler_redo_block(const DrCfgPrepared<float> *cfg, uint64_t seed, uint64_t id,
+                                                       uint32_t call, int j)
+{
+    const DimBlock<float> blk = load_dim_block(*cfg, j);
+    float v[4];
+    const unsigned pending = first_attempt<float>(kDrType, blk, seed, id, call, kTasks, j, v);
+    const unsigned viol = pending ? redraws<float>(kDrType, blk, seed, id, call, kTasks, j, pending, v) : 0u;
+    return RedoneBlock{ v[0], v[1], v[2], v[3], viol };
+}
+
+template <int kDrType, int kStore>
+__global__ void __launch_bounds__(kSampleThreads, RENV_SAMPLER_F32_CTAS)
+dr_sample_f32_kernel(float *__restrict__ out, int64_t n, const __grid_constant__ DrCfgPrepared<float> cfg, uint64_t seed,
+                     const __grid_constant__ PhiloxKeys ks, uint64_t sample_id0, uint32_t call,
+                     unsigned long long *violations, int items)
+{
+    const int dim = cfg.dim;
+    const int kTile = tile_samples<float>(dim, items);
+    const int blocks_per_sample = (dim + 3) / 4;
+    int log2pad = 0;
+    while ((1 << log2pad) < blocks_per_sample) ++log2pad;
+    const int j = threadIdx.x & ((1 << log2pad) - 1);
+    const int lane_sample = threadIdx.x >> log2pad, samples_per_pass = kSampleThreads >> log2pad;
+    const int64_t first = (int64_t)blockIdx.x * kTile;
+    const int samples = (int)min((int64_t)kTile, n - first);
+    if (j >= blocks_per_sample || lane_sample >= samples) return;
+    const DimBlockPacked pb = pack_dim_block(load_dim_block(cfg, j));
+    // `ks`: the ten round keys, computed on the host -- as kernel parameters they are constant-bank operands of the
+    // Philox XORs (computed here they either occupy 20 registers or are re-added inside the loop, 18 instructions)
+    unsigned viol = 0;
+    float *row = out + (first + lane_sample) * dim + j * 4;
+    const int64_t row_step = (int64_t)samples_per_pass * dim;
+    const uint64_t id0 = sample_id0 + (uint64_t)(first + lane_sample);
+    int todo = (samples - lane_sample + samples_per_pass - 1) / samples_per_pass;      // samples of this thread
+    // samples before the low id word wraps (usually all of them)
+    const uint64_t to_wrap = (0x100000000ull - (id0 & 0xffffffffull) + (uint64_t)samples_per_pass - 1) / (uint64_t)samples_per_pass;
+    uint64_t id = id0;
+    while (todo > 0) {
+        const int seg = (int)min((uint64_t)todo, id == id0 ? to_wrap : (uint64_t)todo);    // a tile wraps at most once
+        // constant words of the segment's counters: (id hi | tick hi, tick lo, purpose | slot)
+        const uint32_t c1 = (uint32_t)(id >> 32) & 0xffffu, c2 = call, c3 = ((uint32_t)kTasks << 24) | (uint32_t)j;
+        uint32_t c0 = (uint32_t)id;
+#pragma unroll 1
+        for (int k = seg; k > 0; --k) {
+            const uint4 r = philox4x32_10(make_uint4(c0, c1, c2, c3), ks);
+            float v[4];
+            if (first_attempt_packed<kDrType>(r, pb, v)) {         // rare
+                const RedoneBlock b = sampler_redo_block<kDrType>(&cfg, seed, (id & ~0xffffffffull) | c0, call, j);
+                v[0] = b.v0; v[1] = b.v1; v[2] = b.v2; v[3] = b.v3;
+                viol += b.viol;
+            }
+            store_block<float, kStore>(row, v, pb.valid);
+            c0 += (uint32_t)samples_per_pass;
+            row += row_step;
+        }
+        id += (uint64_t)seg * (uint64_t)samples_per_pass;
+        todo -= seg;
+    }
+    if (kDrType == kDrGaussian && viol && violations) atomicAdd(violations, (unsigned long long)viol);
+}
+
 // ------------------------------------------------------------------------------------------------
 // sample_tasks(n) for dr_type 'fullgaussian' (random_env.py:192-198): x = mean + F z, clip [0,4], denormalise
 // ------------------------------------------------------------------------------------------------

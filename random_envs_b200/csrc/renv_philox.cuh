@@ -33,6 +33,28 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
     return c;
 }
 
+// The same function with the ten round keys precomputed (a loop over many counters with one key: the samplers).
+struct PhiloxKeys { uint32_t x[10], y[10]; };
+__host__ __device__ __forceinline__ PhiloxKeys philox_keys(uint32_t kx, uint32_t ky)
+{
+    constexpr uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    PhiloxKeys ks;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { ks.x[r] = kx + (uint32_t)r * W0; ks.y[r] = ky + (uint32_t)r * W1; }
+    return ks;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &ks)
+{
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ ks.x[r], lo1, hi0 ^ c.w ^ ks.y[r], lo0);
+    }
+    return c;
+}
+
 // One 128-bit block of the stream (seed, id, tick, purpose); slot = attempt * 16 + dim_block.
 __device__ __forceinline__ uint4 draw_block(uint64_t seed, uint64_t id, uint64_t tick, uint32_t purpose, uint32_t slot)
 {

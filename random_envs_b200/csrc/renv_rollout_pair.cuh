@@ -17,31 +17,9 @@
 // for several parked slots (see cartpole_rollout_kernel); a slot that finishes its K steps stores its env at once.
 #pragma once
 #include "renv_kernels.cuh"
+#include "renv_pack.cuh"
 
 namespace renv {
-
-using u64 = unsigned long long;
-
-__device__ __forceinline__ u64 pk(float lo, float hi)
-{
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
-{
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b)
-{
-    u64 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 splat(float v) { return pk(v, v); }
 
 #ifndef RENV_PAIR_RESET_BATCH
 #define RENV_PAIR_RESET_BATCH 16
