@@ -54,11 +54,18 @@ def test_fp32_rollout_runs_on_the_packed_fp32_pipe_and_fp64_rollout_on_dfma(sass
 
 
 def test_uniform_sampler_loop_is_philox_plus_conversion_only(sass):
-    rows = _one(sass, "dr_sample_kernelIfLi1ELi0")                  # <float, uniform, 128-bit stores>
+    rows = _one(sass, "dr_sample_f32_kernelILi1ELi0")               # <uniform, 128-bit stores>
     ops = _ops(rows)
-    assert sum(o.startswith("IMAD.WIDE.U32") for o in ops) >= 19   # Philox4x32-10: 2 per round
+    assert 17 <= sum(o.startswith("IMAD.WIDE.U32") for o in ops) <= 24    # Philox4x32-10 with the first rounds' constants hoisted
     assert not any(o.startswith("F2F") for o in ops)               # parameters arrive converted (host side)
+    assert sum(o.startswith("FFMA2") for o in ops) >= 2            # packed affine map
     assert any(o.startswith("STG.E.128") for o in ops)
+    assert not any(o.startswith(("STL", "LDL")) for o in ops)      # no stack traffic
+    for kind in ("Li2ELi1", "Li3ELi1"):                            # truncnorm / gaussian, 30-dim store shape
+        tn = _ops(_one(sass, "dr_sample_f32_kernelI" + kind))
+        assert sum(o.startswith("FFMA2") for o in tn) >= 2 and sum(o.startswith("FMUL2") for o in tn) >= 2
+    f64 = _ops(_one(sass, "dr_sample_kernelIdLi1ELi0"))             # fp64 keeps the generic kernel
+    assert sum(o.startswith("IMAD.WIDE.U32") for o in f64) >= 19
 
 
 def test_no_register_spills_in_the_rollout_kernels():
