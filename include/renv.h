@@ -117,9 +117,13 @@ int renv_abi_version(void);
 const char *renv_strerror(int code);
 
 /* RandomEnv.sample_tasks(n) -> (n, dim) row-major  (random_env.py:145-203).
- * Sample i uses Philox id = sample_id0 + i and episode field = call.  `violations` (may be NULL)
- * counts gaussian dims whose three draws were all < 0.1 -- the host raises the reference's
- * Exception('Not all samples were above > 0.1 after 2 attempts') when it is non-zero. */
+ * Sample i uses Philox id = sample_id0 + i and episode field = call.  `violations` (may be NULL) is the
+ * RENV_NUM_COUNTERS-element counter array of the Conventions: [0] counts gaussian dims whose three draws were all
+ * < 0.1 -- the host raises the reference's Exception('Not all samples were above > 0.1 after 2 attempts') when it
+ * is non-zero.
+ * dr_type fullgaussian with 17 <= dim <= 32 in fp32 runs its (n x 32) . (32 x 32) contraction on the tensor cores
+ * (tcgen05.mma kind::tf32, split into head and tail: fp32-grade products, fp32 accumulation); smaller dims and fp64
+ * use FMA chains.  Both draw the same normals; the results agree to 4e-6 of the search-bound width. */
 int renv_dr_sample_f32(float *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0,
                        uint32_t call, unsigned long long *violations, void *stream);
 int renv_dr_sample_f64(double *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0,

