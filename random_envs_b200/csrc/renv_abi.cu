@@ -147,7 +147,13 @@ bool launch_fullgaussian_tc(float *out, int64_t n, const FullGaussCfg<float> &g,
     if (e != cudaSuccess) { *rc = (int)e; return true; }
     const int64_t tiles = (n + kFgTile - 1) / kFgTile;
     const int64_t grid = tiles < (int64_t)sms * RENV_FG_TC_CTAS ? tiles : (int64_t)sms * RENV_FG_TC_CTAS;
-    dr_sample_fullgaussian_tc_kernel<<<(unsigned)grid, kFgThreads, 0, st>>>(out, n, g, seed, sample_id0, call, counters);
+    FullGaussCfg<float> gt = g;
+    for (int k = 0; k < 32; ++k) {      // the kernel's epilogue takes the WIDTH hi - lo (rounded once, as denormalize does) and mean / 4 (exact)
+        gt.hi[k] = g.hi[k] - g.lo[k];
+        gt.mean[k] = 0.25f * g.mean[k];
+    }
+    const PhiloxKeys ks = philox_keys((uint32_t)seed, (uint32_t)(seed >> 32));
+    dr_sample_fullgaussian_tc_kernel<<<(unsigned)grid, kFgThreads, 0, st>>>(out, n, gt, ks, sample_id0, call, counters);
     *rc = launch_status();
     return true;
 }

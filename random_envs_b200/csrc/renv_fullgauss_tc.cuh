@@ -4,20 +4,24 @@
 //     X (128 samples x 32) = Z (128 x 32 standard normals) . F^T (32 x 32),   F F^T = cov
 //
 // is the one GEMM-shaped piece of the hot path (2 dim^2 FLOPs per sample: on CUDA cores it made the 30-dim sampler
-// FMA-bound at 0.20 of the HBM rate, round-1 verdict).  Per 128-sample tile of a persistent CTA (128 threads):
+// FMA-bound at 0.20 of the HBM rate, round-1 verdict).  Per 128-sample tile of a persistent CTA (128 threads, one per
+// sample; a 256-thread variant in which threads t and t + 128 share TMEM lane t and split the k / d range in halves
+// was measured slower: 1.17 vs 1.03 ms for 2^24 x 30 -- the work per sample is the same and the barriers double):
 //
-//   1. thread t draws the 32 normals of sample t (the SAME Philox blocks and Box-Muller as the CUDA-core kernel:
-//      draw_block(seed, id, call, kTasks, j), j = 0..7) and writes them -- split into a TF32 head and a TF32 tail,
-//      z = z_hi + z_lo -- straight from registers into TENSOR MEMORY with tcgen05.st: row t of the A operand is
-//      TMEM lane t, element k is column k.  Z never touches shared or global memory.
+//   1. the thread(s) of sample t draw its 32 normals (the SAME Philox blocks and Box-Muller as the CUDA-core
+//      kernel: draw_block(seed, id, call, kTasks, j), j = 0..7) and write them -- split into a TF32 head and a TF32
+//      tail, z = z_hi + z_lo -- straight from registers into TENSOR MEMORY with tcgen05.st: row t of the A operand
+//      is TMEM lane t, element k is column k.  Z never touches shared or global memory.
 //   2. one thread issues 12 tcgen05.mma.kind::tf32 (M = 128, N = 32, K = 8; A from TMEM, B = F from shared memory
 //      through a K-major no-swizzle matrix descriptor): for each of the 4 K-steps  D += Z_lo F_hi,  D += Z_hi F_lo,
 //      D += Z_hi F_hi  ("3xTF32": the dropped Z_lo F_lo term is 2^-22 relative, i.e. fp32-grade products with fp32
 //      accumulation in TMEM), then tcgen05.commit -> mbarrier.
-//   3. every thread reads its sample's 32 results back with tcgen05.ld (lane t = sample t), adds the mean, clips to
-//      [0, 4], denormalises to the search bounds and the warp writes its 32 rows as one contiguous span.
+//   3. the threads read their sample's results back with tcgen05.ld (lane t = sample t), add the
+//      mean, clip to [0, 4], denormalise to the search bounds, and each lane quadrant writes its 32 rows as one
+//      contiguous span.  The accumulator is double-buffered: the epilogue of tile i-1 runs while the tensor core
+//      works on tile i, and the wait for tile i's MMAs sits after the NEXT tile's normals have been drawn.
 //
-// TMEM per CTA: 32 (Z_hi) + 32 (Z_lo) + 32 (D) = 96 -> 128 columns allocated: 4 CTAs per SM share the 512 columns.
+// TMEM per CTA: 32 (Z_hi) + 32 (Z_lo) + 2 x 32 (D) = 128 columns: 4 CTAs per SM share the 512 columns.
 // Tolerance against the fp32 FMA-chain kernel (same draws): <= 4e-6 of the search-bound width (tests/test_gpu_fullgaussian.py).
 #pragma once
 #include "renv_kernels.cuh"
@@ -25,9 +29,21 @@
 namespace renv {
 
 constexpr int kFgTile = 128;            // samples per tile = MMA M = TMEM lanes
-constexpr int kFgThreads = 128;
-constexpr int kFgTmemCols = 128;        // allocation (power of two >= 96)
+#ifndef RENV_FG_TC_THREADS
+#define RENV_FG_TC_THREADS 128
+#endif
+constexpr int kFgThreads = RENV_FG_TC_THREADS;      // 128: one thread per sample; 256: two (k / d halves), see below
+constexpr int kFgSplit = kFgThreads / 128;          // threads per sample
+constexpr int kFgPer = 32 / kFgSplit;               // normals / outputs per thread
+static_assert(kFgThreads == 128 || kFgThreads == 256, "one or two threads per sample");
+constexpr int kFgTmemCols = 128;        // Z_hi 32 + Z_lo 32 + two accumulators of 32
 constexpr uint32_t kFgColZhi = 0, kFgColZlo = 32, kFgColD = 64;
+#ifndef RENV_FG_EXP_PASSES
+#define RENV_FG_EXP_PASSES 3        // experiment knobs (profiles/exp): 1 = head x head only; NOGEN = no Philox / Box-Muller
+#endif
+#ifndef RENV_FG_EXP_NOGEN
+#define RENV_FG_EXP_NOGEN 0
+#endif
 #ifndef RENV_FG_TC_CTAS
 #define RENV_FG_TC_CTAS 4
 #endif
@@ -35,7 +51,7 @@ constexpr uint32_t kFgColZhi = 0, kFgColZlo = 32, kFgColD = 64;
 struct __align__(128) FgTcSmem {
     float b_hi[32 * 32];                // F as the B operand, K-major core-matrix layout (see fg_b_index)
     float b_lo[32 * 32];
-    float stage[kFgThreads * 32];       // per warp: 32 rows of `dim` values, contiguous
+    float stage[kFgTile * 32];          // per lane quadrant: 32 rows of `dim` values, contiguous
     unsigned long long mbar;
     uint32_t tmem_base;
     uint32_t failed;
@@ -85,10 +101,23 @@ __device__ __forceinline__ void fg_tmem_ld32(uint32_t taddr, float *v)
 #pragma unroll
     for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
 }
+__device__ __forceinline__ void fg_tmem_ld16(uint32_t taddr, float *v)
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+}
 
 __global__ void __launch_bounds__(kFgThreads, RENV_FG_TC_CTAS)
 dr_sample_fullgaussian_tc_kernel(float *__restrict__ out, int64_t n, const __grid_constant__ FullGaussCfg<float> cfg,
-                                 uint64_t seed, uint64_t sample_id0, uint32_t call, unsigned long long *counters)
+                                 const __grid_constant__ PhiloxKeys ks, uint64_t sample_id0, uint32_t call,
+                                 unsigned long long *counters)
 {
     __shared__ FgTcSmem sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -117,74 +146,112 @@ dr_sample_fullgaussian_tc_kernel(float *__restrict__ out, int64_t n, const __gri
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);       // this warp's 32 TMEM lanes
+    const int quad = warp & 3, half = warp >> 2;                           // TMEM lane quadrant / which 16 of the 32 k, d
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);       // this warp's 32 TMEM lanes
     const uint64_t desc_hi = fg_smem_desc(sm.b_hi), desc_lo = fg_smem_desc(sm.b_lo);
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&sm.mbar);
+
+    auto wait_mma = [&](uint32_t parity) {      // bounded (an encoding error must not hang the GPU): ~0.2 s, then give up loudly
+        uint32_t ready = 0;
+        for (int spin = 0; !ready && spin < (1 << 22); ++spin)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ready) : "r"(mbar), "r"(parity) : "memory");
+        if (!ready) sm.failed = 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    // rows of tile `tile` out of accumulator `buf`: clip, denormalise, and write the quadrant's 32 rows as one span
+    auto epilogue = [&](int64_t tile, int buf) {
+        float x[kFgPer];
+        if (kFgSplit == 1) fg_tmem_ld32(lane_base + kFgColD + 32 * buf, x);
+        else fg_tmem_ld16(lane_base + kFgColD + 32 * buf + 16 * half, x);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        float *rows = sm.stage + quad * 32 * 32;
+        float *row = rows + lane * dim + kFgPer * half;
+#pragma unroll
+        for (int q = 0; q < kFgPer; ++q) {
+            const int d = kFgPer * half + q;
+            // (clip(mean + x, 0, 4) * width) / 4 + lo (random_env.py:194-198, 205-220) in two instructions: scaling by
+            // 1/4 is exact and commutes with rounding, so sat(x / 4 + mean / 4) == clip(fl(mean + x), 0, 4) / 4 and
+            // fl(q * width) == fl(p * width) / 4 bit for bit; the host passes mean / 4 and width = hi - lo
+            const float q4 = __saturatef(fmaf(x[q], 0.25f, cfg.mean[d]));
+            if (d < dim) row[q] = fmaf(q4, cfg.hi[d], cfg.lo[d]);
+        }
+        if (kFgSplit == 1) __syncwarp();
+        else asm volatile("bar.sync %0, 64;" :: "r"(1 + quad) : "memory");    // both halves of the quadrant have written
+        const int64_t quad_first = tile * kFgTile + quad * 32;
+        const int nrows = (int)max((int64_t)0, min((int64_t)32, n - quad_first));
+        const int total = nrows * dim;
+        float *dst = out + quad_first * dim;                        // 32 * dim * 4 bytes is a multiple of 128
+        const int nvec = total / 4, t0 = half * 32 + lane;
+        for (int q = t0; q < nvec; q += 32 * kFgSplit)
+            reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(rows)[q];
+        for (int q = nvec * 4 + t0; q < total; q += 32 * kFgSplit) dst[q] = rows[q];
+        if (kFgSplit == 1) __syncwarp();
+        else asm volatile("bar.sync %0, 64;" :: "r"(1 + quad) : "memory");    // the stage may be rewritten
+    };
 
     const int64_t num_tiles = (n + kFgTile - 1) / kFgTile;
-    uint32_t phase = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t i = tile * kFgTile + tid;
+    int it = 0;
+    int64_t prev_tile = -1;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int64_t i = tile * kFgTile + quad * 32 + lane;
         const uint64_t id = sample_id0 + (uint64_t)i;
 
-        // ---- 1. Z -> TMEM (head and tail), 8 columns at a time
+        // ---- 1. this thread's normals (Philox blocks kFgPer/4 * half ...), split into TF32 head and tail
+        float hi[kFgPer], lo[kFgPer];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            float z[8], hi[8], lo[8];
-            Num<float>::normals(draw_block(seed, id, call, kTasks, (uint32_t)j), z);
-            Num<float>::normals(draw_block(seed, id, call, kTasks, (uint32_t)j + 1u), z + 4);
+        for (int j = 0; j < kFgPer / 4; ++j) {
+            float z[4];
+#if RENV_FG_EXP_NOGEN
+            z[0] = (float)lane; z[1] = (float)j; z[2] = 1.0f; z[3] = (float)(id & 7);
+#else
+            // draw_block(seed, id, call, kTasks, slot) with the round keys as constant-bank operands
+            const uint32_t c1 = (uint32_t)(id >> 32) & 0xffffu, c3 = ((uint32_t)kTasks << 24) | (uint32_t)(kFgPer / 4 * half + j);
+            Num<float>::normals(philox4x32_10(make_uint4((uint32_t)id, c1, call, c3), ks), z);
+#endif
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                hi[q] = __uint_as_float(__float_as_uint(z[q]) & 0xffffe000u);
-                lo[q] = z[q] - hi[q];
+            for (int q = 0; q < 4; ++q) {
+                hi[4 * j + q] = __uint_as_float(__float_as_uint(z[q]) & 0xffffe000u);
+                lo[4 * j + q] = z[q] - hi[4 * j + q];
             }
-            fg_tmem_st8(lane_base + kFgColZhi + 4 * j, hi);
-            fg_tmem_st8(lane_base + kFgColZlo + 4 * j, lo);
+        }
+        // the previous tile's MMAs must have read Z before it is overwritten (they finished long ago: they ran while
+        // the normals above were drawn); its accumulator is then ready for the epilogue further down
+        if (it > 0) wait_mma((uint32_t)(it - 1) & 1u);
+#pragma unroll
+        for (int q = 0; q < kFgPer; q += 8) {
+            fg_tmem_st8(lane_base + kFgColZhi + kFgPer * half + q, hi + q);
+            fg_tmem_st8(lane_base + kFgColZlo + kFgPer * half + q, lo + q);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
 
-        // ---- 2. D = Z F^T on the tensor core
+        // ---- 2. D[it & 1] = Z F^T on the tensor core
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_col = tmem + kFgColD + 32 * (it & 1);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {               // K-step s: columns 8 s .. 8 s + 7 of Z, 256 bytes further into B
                 const uint64_t off = (uint64_t)((256u * s) >> 4);
-                fg_mma(tmem + kFgColD, tmem + kFgColZlo + 8 * s, desc_hi + off, s > 0);
-                fg_mma(tmem + kFgColD, tmem + kFgColZhi + 8 * s, desc_lo + off, true);
-                fg_mma(tmem + kFgColD, tmem + kFgColZhi + 8 * s, desc_hi + off, true);
+#if RENV_FG_EXP_PASSES == 1
+                fg_mma(d_col, tmem + kFgColZhi + 8 * s, desc_hi + off, s > 0);
+#else
+                fg_mma(d_col, tmem + kFgColZlo + 8 * s, desc_hi + off, s > 0);
+                fg_mma(d_col, tmem + kFgColZhi + 8 * s, desc_lo + off, true);
+                fg_mma(d_col, tmem + kFgColZhi + 8 * s, desc_hi + off, true);
+#endif
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                         :: "r"((uint32_t)__cvta_generic_to_shared(&sm.mbar)) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
         }
-        {   // bounded wait (a descriptor or encoding error must not hang the GPU): ~0.2 s, then give up loudly
-            uint32_t ready = 0;
-            for (int spin = 0; !ready && spin < (1 << 22); ++spin)
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(ready) : "r"((uint32_t)__cvta_generic_to_shared(&sm.mbar)), "r"(phase) : "memory");
-            if (!ready) sm.failed = 1;
-        }
-        phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // ---- 3. epilogue: lane t = sample t
-        float x[32];
-        fg_tmem_ld32(lane_base + kFgColD, x);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        float *tile_stage = sm.stage + warp * 32 * 32;
-#pragma unroll
-        for (int d = 0; d < 32; ++d)
-            if (d < dim) tile_stage[lane * dim + d] = denormalize(__fadd_rn(cfg.mean[d], x[d]), cfg.lo[d], cfg.hi[d]);
-        __syncwarp();
-        const int64_t warp_first = tile * kFgTile + warp * 32;
-        const int rows = (int)max((int64_t)0, min((int64_t)32, n - warp_first));
-        const int total = rows * dim;
-        float *dst = out + warp_first * dim;                        // 32 * dim * 4 bytes is a multiple of 128
-        const int nvec = total / 4;
-        for (int q = lane; q < nvec; q += 32)
-            reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(tile_stage)[q];
-        for (int q = nvec * 4 + lane; q < total; q += 32) dst[q] = tile_stage[q];
-        __syncwarp();
+        // ---- 3. epilogue of the PREVIOUS tile while the tensor core works on this one
+        if (it > 0) epilogue(prev_tile, (it - 1) & 1);
+        prev_tile = tile;
+    }
+    if (it > 0) {
+        wait_mma((uint32_t)(it - 1) & 1u);
+        epilogue(prev_tile, (it - 1) & 1);
     }
 
     // ---- teardown

@@ -68,6 +68,15 @@ def test_uniform_sampler_loop_is_philox_plus_conversion_only(sass):
     assert sum(o.startswith("IMAD.WIDE.U32") for o in f64) >= 19
 
 
+def test_fullgaussian_contraction_runs_on_tcgen05(sass):
+    """The one GEMM-shaped op of the path: UTC*MMA (tcgen05.mma), STTM / LDTM (tcgen05.st / .ld), TMEM allocation."""
+    ops = _ops(_one(sass, "dr_sample_fullgaussian_tc_kernel"))
+    assert sum(o.startswith("UTCHMMA") for o in ops) == 12         # 4 K-steps x 3 (head/tail split) per 128-sample tile
+    assert sum(o.startswith("STTM") for o in ops) >= 8 and sum(o.startswith("LDTM") for o in ops) >= 1
+    assert any(o.startswith("UTCBAR") for o in ops)                # tcgen05.commit -> mbarrier
+    assert not any(o.startswith(("HMMA", "STL", "LDL")) for o in ops)
+
+
 def test_no_register_spills_in_the_rollout_kernels():
     path = os.path.join(ROOT, "random_envs_b200", "librenv_b200.ptxas.log")
     if not os.path.isfile(path):
