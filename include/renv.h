@@ -206,6 +206,36 @@ int renv_cartpole_rollout_noisy_f64(const renv_cartpole_env *env, const renv_obs
                                     int K, int integrator, int max_steps, uint64_t tick, const renv_dr_cfg *dr,
                                     double *stats, unsigned long long *violations, void *stream);
 
+/* The SCALAR drop-in env (gym.make('RandomCartPole-v0'): RandomCartPoleEnv.step / reset, random_cartpole.py:172-229,
+ * one env, one host call per step) served by a resident one-warp kernel instead of one launch + synchronise per call.
+ * `ctrl` is PINNED, DEVICE-MAPPED HOST memory (zero-initialised once): the host rings a request in by writing
+ * `request = (seq << 8) | op` (seq grows by 1 per request, 24 bits; op 0 / 1 = step(action); 2 = reset, 3 = set state,
+ * 4 = set xi, 5 = configure, 6 = exit, each reading the `arg` / `arg_u64` fields that the host wrote BEFORE the request
+ * word -- see csrc/renv_scalar_server.cuh for the field meanings) and spins on `ack == seq`; the results are in
+ * state / obs / xi / reward / done / beyond / violations.  `save` is RENV_SCALAR_SAVE_BYTES of zero-initialised DEVICE
+ * memory that carries the env between kernel instances: the kernel is a lease -- after `lease_ns` without a request it
+ * stores its registers there, sets ctrl->exited = lease_id and exits; the caller launches the next instance (lease_id
+ * + 1) when it has a request and sees exited == the id it launched last.  One instance at a time per ctrl block. */
+#define RENV_SCALAR_SAVE_BYTES 512
+typedef struct renv_scalar_ctrl {
+    uint32_t request;            /* host -> device */
+    uint32_t pad0[15];
+    double arg[16];              /* host -> device: arguments of ops >= 2 */
+    uint64_t arg_u64[8];
+    double state[4];             /* device -> host: x, x_dot, theta, theta_dot after the request */
+    double obs[4];               /*   Noisy variant: state + sqrt(noise_level) N(0, I) */
+    double xi[4];                /*   gravity, cart_mass, pole_mass, pole_length (written by ops >= 2) */
+    double reward;
+    int32_t done;
+    int32_t beyond;              /*   steps_beyond_done, -1 == None */
+    uint32_t violations;         /*   gaussian DR dims that failed three times (reset with resample) */
+    uint32_t pad1;
+    uint32_t ack;                /* device -> host: seq of the last request served */
+    uint32_t exited;             /* device -> host: lease id of the instance that has exited */
+    uint32_t pad2[14];
+} renv_scalar_ctrl;
+int renv_cartpole_scalar_serve(renv_scalar_ctrl *ctrl, void *save, uint32_t lease_id, uint64_t lease_ns, void *stream);
+
 /* action_space.sample() for n envs (test_random_policy.py:26): Bernoulli(1/2) bits of Philox block
  * (env_id >> 7, tick = step). */
 int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step,

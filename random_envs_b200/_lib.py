@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("RENV_B200_LIB", os.path.join(_HERE, "librenv_b200.so"
 ABI_VERSION = 5
 MAX_DIM = 32
 NUM_STATS = 6
+SCALAR_SAVE_BYTES = 512     # RENV_SCALAR_SAVE_BYTES
 COUNTER_GAUSSIAN, COUNTER_BAD_ACTION, COUNTER_ORDER_TIMEOUT = 0, 1, 2
 TILE_ENVS = {'float32': 1024, 'float64': 512}      # RENV_TILE_ENVS_F32 / _F64
 NUM_COUNTERS = 3          # [0] gaussian draws exhausted, [1] invalid actions (include/renv.h)
@@ -67,6 +68,7 @@ SIGNATURES = {
     "renv_cartpole_rollout_f64": (_int, [_env_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_cartpole_rollout_noisy_f32": (_int, [_env_p, _noise_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_cartpole_rollout_noisy_f64": (_int, [_env_p, _noise_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
+    "renv_cartpole_scalar_serve": (_int, [_vp, _vp, _u32, _u64, _vp]),
     "renv_random_actions_u8": (_int, [_vp, _i64, _u64, _u64, _u32, _vp]),
 }
 

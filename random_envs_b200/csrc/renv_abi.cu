@@ -4,6 +4,7 @@
 #include "renv_kernels.cuh"
 #include "renv_rollout_pair.cuh"
 #include "renv_fullgauss_tc.cuh"
+#include "renv_scalar_server.cuh"
 #include <stdlib.h>
 
 #ifndef RENV_ROLLOUT_F32_PAIR
@@ -476,6 +477,16 @@ int renv_cartpole_rollout_noisy_f64(const renv_cartpole_env *env, const renv_obs
 {
     if (noise == nullptr) return RENV_E_NULL;
     return cartpole_rollout<double>(env, noise, w, b, K, integrator, max_steps, tick, dr, stats, violations, stream);
+}
+
+int renv_cartpole_scalar_serve(renv_scalar_ctrl *ctrl, void *save, uint32_t lease_id, uint64_t lease_ns, void *stream)
+{
+    if (ctrl == nullptr || save == nullptr) return RENV_E_NULL;
+    if (!aligned(ctrl, 64) || !aligned(save, 16)) return RENV_E_ALIGN;
+    if (lease_ns == 0 || lease_ns > 1000000000ull) return RENV_E_ARG;      // a lease, not a daemon: at most 1 s idle
+    cartpole_scalar_server_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ctrl, static_cast<ScalarSave *>(save),
+                                                                                 lease_id, lease_ns);
+    return launch_status();
 }
 
 int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step, void *stream)

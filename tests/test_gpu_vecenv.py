@@ -50,9 +50,11 @@ def test_reset_and_step_contract(dtype):
         small.step([0, 1])
     with pytest.raises(AssertionError, match="invalid"):
         small.step(torch.tensor([0.0, 1.0, 1.0]))
-    strict = random_envs.RandomCartPoleVecEnv(3, validate_actions=True); strict.reset()
+    # an action outside Discrete(2) is flagged by the step kernel and raised at the next synchronising call
+    strict = random_envs.RandomCartPoleVecEnv(3); strict.reset()
+    strict.step([0, 2, 1])
     with pytest.raises(AssertionError, match="invalid"):
-        strict.step([0, 2, 1])
+        strict.check_dr_violations()
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
@@ -362,3 +364,46 @@ def test_in_place_edits_of_the_distribution_arrays_take_effect():
     env.step(env.sample_actions())
     g = _np(env.get_task())[:, 0]
     assert g.min() >= 30.0 and g.max() <= 31.0
+
+
+def test_resident_scalar_env_equals_the_launch_per_step_path_and_sample_task(monkeypatch):
+    """The drop-in gym env is served by a resident kernel (renv_cartpole_scalar_serve); RENV_SCALAR_RESIDENT=0 is the
+    launch-per-step path.  Same seed -> the same episodes bit for bit, including the xi drawn on reset, which equals
+    what RandomEnv.sample_task() returns for the same call index."""
+    def run(resident, dr_type, distr, noisy=False):
+        monkeypatch.setenv("RENV_SCALAR_RESIDENT", "1" if resident else "0")
+        env = random_envs.RandomCartPoleEnv(noisy=noisy)
+        env.seed(5)
+        env.set_dr_distribution(dr_type, distr); env.set_dr_training(True)
+        rs = np.random.RandomState(1)
+        out = [env.reset().copy(), env.get_task().copy()]
+        for k in range(150):
+            o, r, d, _ = env.step(int(rs.randint(2)))
+            out.append(np.concatenate([o, [r, float(d)]]))
+            if d and k % 3 == 0:
+                out.append(env.reset().copy()); out.append(env.get_task().copy())
+        env.close()
+        return out
+    cases = [("uniform", SEARCH, False), ("truncnorm", [9.8, 0.98, 1.0, 0.1, 0.11, 0.02, 0.5, 0.05], False),
+             ("gaussian", [9.8, 0.98, 1.0, 0.1, 0.2, 0.02, 0.5, 0.05], True)]
+    for dr_type, distr, noisy in cases:
+        a, b = run(True, dr_type, distr, noisy), run(False, dr_type, distr, noisy)
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)), dr_type
+    monkeypatch.setenv("RENV_SCALAR_RESIDENT", "1")
+    e1, e2 = random_envs.RandomCartPoleEnv(), random_envs.RandomCartPoleEnv()
+    for e in (e1, e2):
+        e.seed(9); e.set_dr_distribution("uniform", SEARCH); e.set_dr_training(True)
+    e1.reset()
+    assert np.array_equal(e1.get_task(), e2.sample_task())           # call index 0 of the same Philox stream
+    e1.reset()
+    assert np.array_equal(e1.get_task(), e2.sample_task())           # call index 1
+    # the lease: an idle env parks itself and is revived transparently
+    import time
+    s_before = e1.state
+    time.sleep(0.01)
+    o, r, d, _ = e1.step(1)
+    assert e1._core.exited[0] != 0 and np.all(np.isfinite(o)) and e1.state != s_before
+    with pytest.raises(Exception, match="Not all samples were above"):
+        bad = random_envs.RandomCartPoleEnv()
+        bad.set_dr_distribution("gaussian", [-5.0, 0.1, 1.0, 0.1, 0.1, 0.01, 0.5, 0.05]); bad.set_dr_training(True)
+        bad.reset()
