@@ -236,8 +236,8 @@ typedef struct renv_scalar_ctrl {
 } renv_scalar_ctrl;
 int renv_cartpole_scalar_serve(renv_scalar_ctrl *ctrl, void *save, uint32_t lease_id, uint64_t lease_ns, void *stream);
 
-/* action_space.sample() for n envs (test_random_policy.py:26): Bernoulli(1/2) bits of Philox block
- * (env_id >> 7, tick = step). */
+/* action_space.sample() for n envs (test_random_policy.py:26): env e at clock `step` takes bit (step & 127) of its own
+ * Philox block (e, step >> 7), purpose 2 -- one block holds an env's Bernoulli(1/2) actions for 128 consecutive steps. */
 int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step,
                            void *stream);
 

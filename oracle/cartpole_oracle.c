@@ -153,14 +153,16 @@ void oracle_uniforms_f32(uint64_t seed, uint64_t id, uint64_t ep, uint32_t purpo
     for (int k = 0; k < dim; ++k) out[k] = uniform_f32(seed, id, ep, purpose, t, k);
 }
 
-/* Bernoulli(1/2) actions: env e at step t uses bit (e & 127) of the 128-bit block (e >> 7, t) */
+/* Bernoulli(1/2) actions: env e at step t uses bit (t & 127) of ITS 128-bit block (e, t >> 7): one Philox block
+ * carries an env's actions for 128 consecutive steps (a fused rollout draws one block per 128 env-steps) */
 void oracle_random_actions(int64_t n, uint64_t env_id0, uint64_t seed, uint64_t step, uint8_t *out)
 {
+    step &= 0xffffffffull;
     for (int64_t i = 0; i < n; ++i) {
         uint64_t e = env_id0 + (uint64_t)i;
         uint32_t r[4];
-        draw(seed, e >> 7, step, PURPOSE_ACTION, 0, r);
-        out[i] = (uint8_t)((r[(e >> 5) & 3] >> (e & 31)) & 1u);
+        draw(seed, e, step >> 7, PURPOSE_ACTION, 0, r);
+        out[i] = (uint8_t)((r[(step >> 5) & 3] >> (step & 31)) & 1u);
     }
 }
 

@@ -493,8 +493,8 @@ int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_
 {
     if (action == nullptr) return RENV_E_NULL;
     if (n <= 0) return RENV_E_SIZE;
-    if (!aligned(action, 16)) return RENV_E_ALIGN;
-    const int64_t threads = (n + 15) / 16;
+    if (!aligned(action, 4)) return RENV_E_ALIGN;
+    const int64_t threads = (n + 3) / 4;
     const int64_t blocks = (threads + 255) / 256;
     if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
     random_actions_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(action, n, env_id0, seed, step);

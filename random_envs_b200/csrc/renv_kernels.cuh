@@ -180,7 +180,7 @@ constexpr int kStepThreads = RENV_STEP_THREADS;
 //     of which hung), and CTAs that step 2 or 4 tiles (a loop makes ptxas spill the freshly loaded rows; straight-line
 //     copies blow the instruction cache: 16 us).
 template <typename T, bool kAutoReset, bool kNoisy = false, bool kLean = false>
-__global__ void __launch_bounds__(kStepThreads, RENV_STEP_MIN_CTAS(T)) cartpole_step_kernel(const __grid_constant__ StepArgs<T> a)
+__global__ void __launch_bounds__(kStepThreads, kNoisy ? (sizeof(T) == 8 ? 2 : 3) : RENV_STEP_MIN_CTAS(T)) cartpole_step_kernel(const __grid_constant__ StepArgs<T> a)
 {
     using VT = VecTraits<T>;
     constexpr int V = VT::V;
@@ -471,6 +471,7 @@ template <typename T> struct RolloutArgs {
 // (kResetBatch) instead of once per finished lane with one lane active.  A parked lane simply resumes later and
 // runs its remaining steps after the others, so every env still performs exactly K steps with the same
 // (seed, id, tick) draws: results are bit-identical to K single-step launches.
+struct ActionBits { uint4 r; uint32_t group; };     // an env's 128 action bits for steps 128 g .. 128 g + 127 (random policy)
 template <typename T> struct RolloutThread {
     State<T> s; Xi<T> p; Derived<T> d;
     int32_t el; uint32_t new_episodes; bool xi_dirty;
@@ -482,6 +483,7 @@ template <typename T> struct RolloutThread {
     // (0: a step's observation, 1: a reset's) -- exactly what step() / reset() wrote for that tick.
     State<T> obs0; bool obs_loaded; uint32_t after_reset;
     unsigned long long sum_r2; unsigned sum_r; float min_r, max_r; unsigned episodes, sum_len, viol;
+    ActionBits act;     // random policy only: the env's current 128 action bits
 };
 
 #ifndef RENV_RESET_BATCH
@@ -500,14 +502,25 @@ constexpr int kUnrollF64 = RENV_UNROLL_F64;
 #define RENV_ROLLOUT_F64_CTAS 3
 #endif
 
-// Bernoulli(1/2) action of env `id` at clock `tick`: bit (id & 127) of Philox block (id >> 7, tick) -- the bit
-// random_actions_kernel writes for that env and tick, so a random-policy rollout equals K x step(sample_actions()).
-__device__ __forceinline__ int random_action(uint64_t seed, uint64_t id, uint64_t tick)
+// Bernoulli(1/2) action of env `id` at clock `step` (low 32 bits of the tick): bit (step & 127) of the env's OWN Philox
+// block (id, step >> 7) -- the bit random_actions_kernel writes for that env and tick, so a random-policy rollout equals
+// K x step(sample_actions()).  One block carries an env's actions for 128 consecutive steps: the fused rollout keeps it
+// in registers and draws a new one every 128 env-steps (round 1 keyed the block by (id >> 7, step): every env-step
+// re-derived a whole block for one bit, and the random-policy rollout ran at 0.11 of the FMA peak).
+__device__ __forceinline__ uint32_t action_bit(const uint4 &r, uint32_t step)
 {
-    const uint4 r = draw_block(seed, id >> 7, tick & 0xffffffffull, kAction, 0);
-    const uint32_t sel = (uint32_t)(id >> 5) & 3u;
+    const uint32_t sel = (step >> 5) & 3u;
     const uint32_t word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
-    return (int)((word >> (id & 31)) & 1u);
+    return (word >> (step & 31u)) & 1u;
+}
+__device__ __forceinline__ int random_action(ActionBits &c, uint64_t seed, uint64_t id, uint64_t tick)
+{
+    const uint32_t step = (uint32_t)tick;
+    if ((step >> 7) != c.group) {
+        c.group = step >> 7;
+        c.r = draw_block(seed, id, (uint64_t)c.group, kAction, 0);
+    }
+    return (int)action_bit(c.r, step);
 }
 
 template <typename T, bool kEuler, bool kKnownSmall, bool kNoisy = false, bool kRandom = false>
@@ -516,7 +529,7 @@ __device__ __forceinline__ void rollout_step(RolloutThread<T> &t, const RolloutA
 {
     int action;
     if (kRandom) {      // action_space.sample() of the reference's demo loop (test_random_policy.py:26), per env and tick
-        action = random_action(a.env.seed, id, a.tick + (uint64_t)(a.K - t.remaining));
+        action = random_action(t.act, a.env.seed, id, a.tick + (uint64_t)(a.K - t.remaining));
     } else if (kNoisy) {       // the policy acts on the OBSERVATION of the current state (what step()/reset() returned for it)
         State<T> o = t.obs0;
         if (!t.obs_loaded) {
@@ -566,7 +579,7 @@ __device__ __forceinline__ float pin(float v) { asm volatile("" : "+f"(v)); retu
 __device__ __forceinline__ double pin(double v) { asm volatile("" : "+d"(v)); return v; }
 
 template <typename T, bool kEuler, bool kNoisy = false, bool kRandom = false>
-__global__ void __launch_bounds__(kRolloutThreads, (sizeof(T) == 4 ? 3 : RENV_ROLLOUT_F64_CTAS))
+__global__ void __launch_bounds__(kRolloutThreads, (sizeof(T) == 4 ? 3 : (kNoisy || kRandom) ? 2 : RENV_ROLLOUT_F64_CTAS))
 cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -585,6 +598,7 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
     t.el = a.env.elapsed[il];
     t.new_episodes = 0; t.xi_dirty = false; t.parked = -1; t.reset_tick = 0;
     t.obs_loaded = kNoisy; t.after_reset = 0u;
+    t.act.group = 0xffffffffu; t.act.r = make_uint4(0, 0, 0, 0);
     if (kNoisy) t.obs0 = State<T>{ a.env.obs[il], a.env.obs[ld + il], a.env.obs[2 * ld + il], a.env.obs[3 * ld + il] };
     else t.obs0 = t.s;
     const uint64_t id = a.env.env_id0 + (uint64_t)il;
@@ -746,7 +760,7 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
 //   * attempt 0 only answers "did any dim fall below its floor" (4 FSETP); the retry loop of the reference, with
 //     its per-dim bookkeeping, is out of line.
 #ifndef RENV_SAMPLER_F32_CTAS
-#define RENV_SAMPLER_F32_CTAS 3
+#define RENV_SAMPLER_F32_CTAS 2      // 90-94 registers: round keys, packed constants and parameters all stay resident
 #endif
 // The reference's retry loop for one block whose first attempt left some dim below its floor (random_env.py:158-171,
 // 177-190): out of line, so that the per-block loop of the kernel stays Philox + packed transform + store.
@@ -890,48 +904,20 @@ dr_sample_fullgaussian_kernel(T *__restrict__ out, int64_t n, const __grid_const
 __global__ void __launch_bounds__(256) random_actions_kernel(uint8_t *__restrict__ action, int64_t n, uint64_t env_id0,
                                                              uint64_t seed, uint32_t step)
 {
-    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i0 >= n) return;
-    uint64_t cached_group = ~0ull;
-    uint4 r = make_uint4(0, 0, 0, 0);
-    uint32_t words[4] = { 0, 0, 0, 0 };
+    uint32_t word = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < 4; ++k) {
         const uint64_t e = env_id0 + (uint64_t)(i0 + k);
-        if ((e >> 7) != cached_group) {
-            cached_group = e >> 7;
-            r = draw_block(seed, cached_group, step, kAction, 0);
-        }
-        const uint32_t sel = (uint32_t)(e >> 5) & 3u;
-        const uint32_t word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
-        const uint32_t bit = (word >> (e & 31)) & 1u;
-        words[k >> 2] |= bit << (8 * (k & 3));
+        const uint4 r = draw_block(seed, e, (uint64_t)(step >> 7), kAction, 0);
+        word |= action_bit(r, step) << (8 * k);
     }
-    if (i0 + 16 <= n) {
-        *reinterpret_cast<uint4 *>(action + i0) = make_uint4(words[0], words[1], words[2], words[3]);
+    if (i0 + 4 <= n) {
+        *reinterpret_cast<uint32_t *>(action + i0) = word;
     } else {
-        for (int k = 0; k < 16 && i0 + k < n; ++k) action[i0 + k] = (uint8_t)((words[k >> 2] >> (8 * (k & 3))) & 1u);
+        for (int k = 0; k < 4 && i0 + k < n; ++k) action[i0 + k] = (uint8_t)((word >> (8 * k)) & 1u);
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// FMA-throughput micro-benchmark (roofline denominator of the fused rollout)
-// ------------------------------------------------------------------------------------------------
-constexpr int kFmaIlp = 8;
-template <typename T> __global__ void fma_peak_kernel(T *out, int iters)
-{
-    T acc[kFmaIlp];
-    const T a = (T)1.0000001, b = (T)1e-7;
-#pragma unroll
-    for (int k = 0; k < kFmaIlp; ++k) acc[k] = (T)(threadIdx.x + k);
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int k = 0; k < kFmaIlp; ++k) acc[k] = acc[k] * a + b;
-    }
-    T sum = 0;
-#pragma unroll
-    for (int k = 0; k < kFmaIlp; ++k) sum += acc[k];
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
 }
 
 }  // namespace renv

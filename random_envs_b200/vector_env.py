@@ -365,6 +365,15 @@ class RandomCartPoleVecEnv(RandomEnv):
         t = _device.torch()
         self._alloc()["stats"].copy_(t.tensor([0.0, 0.0, 0.0, math.inf, -math.inf, 0.0], dtype=t.float64))
 
+    def allgather_stats(self, group=None):
+        """The per-iteration collective (distributed.allgather_stats) on this env's statistics; like every call that
+        synchronises it also surfaces the device-side error flags."""
+        from .distributed import allgather_stats
+        combined, gathered = allgather_stats(self.stats_tensor, group)
+        host = combined.cpu()                   # synchronises
+        self.check_dr_violations()
+        return host, gathered
+
     def episode_stats(self):
         from .distributed import summarize_stats
         stats = self.stats_tensor.cpu().numpy()         # synchronises: the deferred device-side errors surface here

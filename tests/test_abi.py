@@ -69,7 +69,7 @@ def test_strerror_and_argument_validation_without_a_gpu():
     w = (ctypes.c_double * 4)(0, 0, 1, 0)
     assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 0, 0, 500, 0, None, 4096, None, None) == -3
     with pytest.raises(_lib.RenvError, match="alignment"):
-        _lib.call("renv_random_actions_u8", ctypes.c_void_p(4100), 16, 0, 0, 0, None)
+        _lib.call("renv_random_actions_u8", ctypes.c_void_p(4101), 16, 0, 0, 0, None)
 
 
 def test_unknown_dr_type_raises_reference_message():
