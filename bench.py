@@ -343,15 +343,19 @@ def run_b200(args):
 
     # one launch in isolation (sync on both sides, the 4 batches rotating so that it streams from HBM): the number an
     # ncu launch list shows; the amortised figures above overlap consecutive launches
-    iso = []
-    for i in range(40):
+    def bracket(with_kernel, i):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        torch.cuda._sleep(400000)       # ~200 us of busy stream: the launch below is queued before the GPU gets to it,
-        e0.record(); step_g(i); e1.record()     # so the events bracket the kernel and not the host's launch latency
+        torch.cuda._sleep(400000)       # ~200 us of busy stream: what follows is queued before the GPU gets to it,
+        e0.record()                     # so the events bracket the kernel and not the host's launch latency
+        if with_kernel:
+            step_g(i)
+        e1.record()
         torch.cuda.synchronize()
-        iso.append(e0.elapsed_time(e1))
-    iso_us = 1e3 * max_over_ranks(sorted(iso)[len(iso) // 2])
+        return e0.elapsed_time(e1)
+    iso = sorted(bracket(True, i) for i in range(40))
+    empty = sorted(bracket(False, i) for i in range(40))           # the two event records alone
+    iso_us = 1e3 * max_over_ranks(iso[len(iso) // 2] - empty[len(empty) // 2])
 
     peak, peak_src = measured_peaks()
     per_launch_ms = ms / K
@@ -361,7 +365,9 @@ def run_b200(args):
                 "bytes_per_env_step": bytes_per, "launch_us": per_launch_ms * 1e3, "isolated_launch_us": iso_us,
                 "launch_us_note": "launch_us = median graph replay / K with consecutive launches overlapping (amortised); "
                                   "isolated_launch_us = one launch alone on the GPU, nothing before or after it to overlap "
-                                  "with (event-timed behind a spin kernel, so without the host's launch latency)",
+                                  "with (event pair behind a spin kernel minus the same pair with nothing in between; it still "
+                                  "contains the launch ramp of a cold stream -- the ncu launch list under profiles/ has the "
+                                  "kernel-only duration)",
                 "traffic": ncu_traffic(args.dtype)}
 
     def roof(ms_k):

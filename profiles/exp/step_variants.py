@@ -19,6 +19,7 @@ ap.add_argument("--lib", default=None)
 ap.add_argument("--tag", default="default")
 ap.add_argument("--K", type=int, default=400)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--batches", type=int, default=4)
 ap.add_argument("--modes", default="chain,branches,eager,lone,big")
 ap.add_argument("--kernels", default="grid,tile,grid_lean,tile_lean")
 args = ap.parse_args()
@@ -95,14 +96,14 @@ def report(kernel, mode, n, steps, ms_list, bytes_per):
     print(json.dumps({"tag": args.tag, "kernel": kernel, "mode": mode, "n": n, "us_per_launch": round(us, 3),
                       "us_min": round(1e3 * ms_list[0] / steps, 3), "us_max": round(1e3 * ms_list[-1] / steps, 3),
                       "env_steps_per_s": n / us * 1e6, "gbs": round(gbs, 1), "frac": round(gbs / PEAK, 4),
-                      "bytes_per_env_step": bytes_per}), flush=True)
+                      "bytes_per_env_step": bytes_per, "batches": args.batches}), flush=True)
 
 
 modes = args.modes.split(",")
 for kernel in args.kernels.split(","):
     tile, lean = kernel.startswith("tile"), kernel.endswith("lean")
     bytes_per = 54 if lean else 62
-    n, R, K = 1 << 20, 4, args.K
+    n, R, K = 1 << 20, args.batches, args.K
     envs, acts = make(n, R, lean, tile)
 
     def step_i(i):

@@ -9,7 +9,7 @@ import random_envs_b200 as renv  # noqa: E402
 
 dtypes = sys.argv[1:] or ["float32", "float64"]
 for dtype in dtypes:
-    for w in ((0.1, 0.1, 1.0, 0.3), (0.0, 0.0, 1.0, 0.0)):
+    for w in ((0.1, 0.1, 1.0, 0.3), (0.0, 0.0, 1.0, 0.0), None):
         env = renv.RandomCartPoleVecEnv(1 << 24, dtype=dtype, seed=2)
         env.set_dr_distribution("uniform", [2.0, 20.0, 0.5, 3.0, 0.05, 0.3, 0.1, 1.0]); env.set_dr_training(True); env.reset()
         env.rollout(w, 0.0, 10); torch.cuda.synchronize()

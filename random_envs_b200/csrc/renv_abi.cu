@@ -281,7 +281,9 @@ int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, con
     return launch_pdl(cartpole_step_kernel<T, false, true>, (unsigned)blocks, kStepThreads, st, a);
 }
 
-// Random policy (w == NULL): one env per thread, one Philox block per env-step for the action bit.
+// Random policy (w == NULL): one env per thread for both element types (an env draws one Philox block per 128 env-steps
+// for its action bits).  The fp32 env-PAIR kernel was tried for it and is slower (1.4e11 vs 2.4e11 env-steps/s): with
+// ~27-step episodes a pair spends most packed steps with one slot parked for its reset.
 template <typename T> int launch_rollout_random(const RolloutArgs<T> &a, cudaStream_t stream)
 {
     const int64_t blocks = (a.env.n + kRolloutThreads - 1) / kRolloutThreads;
