@@ -7,10 +7,11 @@
 
 One "step" = one pass of the single-step kernel (RandomCartPoleEnv.step + TimeLimit + auto-reset + uniform DR
 resample on reset) over one batch of 2^20 envs -- BASELINE.json configs[1].  Per rank, 4 independent batches
-(248 MB > 126 MB L2) are stepped round-robin so every launch streams its working set from HBM.  The K steps are
-captured once in a CUDA graph (a 10 us kernel is otherwise bound by the Python/ctypes launch path) and the graph is
-replayed >= 200 times (>= 50 ms of timed region) with a CUDA event after every replay: `ms_per_step` is the median
-replay / K, the spread is reported beside it, and the eager public-API rate is reported as `value_eager`.
+(248 MB > 126 MB L2) are stepped round-robin so every launch streams its working set from HBM.  The steps are
+captured in a CUDA graph (a 10 us kernel is otherwise bound by the Python/ctypes launch path); the graph
+holds the K steps ceil(400 / K) times over and is replayed until >= 200 x K steps and >= 50 ms have been timed, with a
+CUDA event after every replay: `ms_per_step` is the median replay / steps in the graph, the spread is reported beside it,
+and the eager public-API rate is reported as `value_eager`.
 
 The reference arm (`--impl reference`) runs the REFERENCE's own RandomCartPoleEnv objects (oracle/_ref, see
 oracle/make_ref.py; the bit-exact port only if those copies are absent) on all host cores for >= 2 s whatever --steps is.
@@ -228,6 +229,10 @@ def run_b200(args):
 
     n, R, A = args.envs, args.batches, 8
     K = args.steps
+    # one captured graph holds K * reps_in_graph steps (>= 400): a 20-step graph is 0.23 ms of GPU work and its replay
+    # rate would measure the host's graph-launch gap, not the kernel
+    reps_in_graph = max(1, -(-400 // K))
+    G = K * reps_in_graph
 
     def make_batches(tile_ordering):
         envs, actions = [], []
@@ -262,14 +267,14 @@ def run_b200(args):
         with torch.cuda.stream(side):
             with torch.cuda.graph(g, stream=side):
                 if not parallel:
-                    for i in range(K):
+                    for i in range(G):
                         step_i(i)
                 else:
                     lanes = [torch.cuda.Stream(device=dev) for _ in range(R)]
                     for b, lane in enumerate(lanes):
                         lane.wait_stream(side)
                         with torch.cuda.stream(lane):
-                            for i in range(b, K, R):
+                            for i in range(b, G, R):
                                 step_i(i)
                     for lane in lanes:
                         side.wait_stream(lane)
@@ -296,8 +301,8 @@ def run_b200(args):
         return per[min(len(per) - 1, int(q * len(per)))]
 
     bytes_per = BYTES_PER_STEP[args.dtype]
-    est_ms = K * n * bytes_per / 5.5e12 * 1e3                       # a first guess of one replay
-    replays = int(max(args.min_replays, -(-args.min_region_ms // est_ms)))
+    est_ms = G * n * bytes_per / 5.5e12 * 1e3                       # a first guess of one replay
+    replays = int(max(-(-args.min_replays // reps_in_graph), -(-args.min_region_ms // est_ms), 10))
 
     # ---- (1) the public API as a user drives it: default env (tile-granular step ordering at this size), ONE stream
     envs_t, actions_t = make_batches("auto")
@@ -335,10 +340,10 @@ def run_b200(args):
     clock_info = clocks.stop(t_wall0, t_wall1) if clocks else None
     ms = max_over_ranks(pct(per, 0.5))              # median replay of the K-step graph
     region_ms = max_over_ranks(region_ms)
-    spread = {"replays": replays, "region_ms": region_ms, "p05_us_per_step": 1e3 * max_over_ranks(pct(per, 0.05)) / K,
-              "p50_us_per_step": 1e3 * ms / K, "p95_us_per_step": 1e3 * max_over_ranks(pct(per, 0.95)) / K,
-              "mean_us_per_step": 1e3 * region_ms / (replays * K)}
-    value = world * n * K / (ms * 1e-3)
+    spread = {"graph_steps": G, "replays": replays, "steps_timed": G * replays, "region_ms": region_ms,
+              "p05_us_per_step": 1e3 * max_over_ranks(pct(per, 0.05)) / G, "p50_us_per_step": 1e3 * ms / G,
+              "p95_us_per_step": 1e3 * max_over_ranks(pct(per, 0.95)) / G, "mean_us_per_step": 1e3 * region_ms / (replays * G)}
+    value = world * n * G / (ms * 1e-3)
     value_eager = world * n * k_eager / (ms_eager * 1e-3)
 
     # one launch in isolation (sync on both sides, the 4 batches rotating so that it streams from HBM): the number an
@@ -358,7 +363,7 @@ def run_b200(args):
     iso_us = 1e3 * max_over_ranks(iso[len(iso) // 2] - empty[len(empty) // 2])
 
     peak, peak_src = measured_peaks()
-    per_launch_ms = ms / K
+    per_launch_ms = ms / G
     achieved = bytes_per * n / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "cartpole_step_kernel<%s>" % ("float" if args.dtype == "float32" else "double"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -370,9 +375,9 @@ def run_b200(args):
                                   "kernel-only duration)",
                 "traffic": ncu_traffic(args.dtype)}
 
-    def roof(ms_k):
-        gbs = bytes_per * n / (ms_k / K * 1e-3) / 1e9
-        return {"launch_us": 1e3 * ms_k / K, "achieved": gbs, "frac": gbs / peak}
+    def roof(ms_g):
+        gbs = bytes_per * n / (ms_g / G * 1e-3) / 1e9
+        return {"launch_us": 1e3 * ms_g / G, "achieved": gbs, "frac": gbs / peak}
 
     # ---- end to end through the public host-buffer API: pinned H2D actions, D2H obs/reward/done every step.
     # The R env batches are stepped round-robin with one step in flight per batch (step_host_async / _wait), so
@@ -423,15 +428,16 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e, "gpu_launches": K * replays,
-            "launch_mode": "one CUDA graph of K cartpole_step_kernel launches, the %d independent env batches on %d "
-                           "parallel graph branches (grid-ordered launches); the graph is replayed %d times back to back "
-                           "(%.0f ms), ms_per_step = median replay / K" % (R, R, replays, region_ms),
+            "config": workload_config(args, world), "clocks": clock_info, "e2e": e2e, "gpu_launches": G * replays,
+            "launch_mode": "one CUDA graph of %d cartpole_step_kernel launches (the K = %d steps x %d), the %d independent "
+                           "env batches on %d parallel graph branches (grid-ordered launches); the graph is replayed %d "
+                           "times back to back (%.0f ms), ms_per_step = median replay / %d"
+                           % (G, K, reps_in_graph, R, R, replays, region_ms, G),
             "timing": spread,
-            "value_eager": value_eager, "value_graph_single_chain": world * n * K / (ms_chain * 1e-3),
+            "value_eager": value_eager, "value_graph_single_chain": world * n * G / (ms_chain * 1e-3),
             "single_stream": {"note": "the default env (tile-granular step ordering, include/renv.h progress) on ONE "
                                       "stream: what a plain step() loop over %d env batches gets" % R,
-                              "eager_python_loop": roof(ms_eager * K / k_eager), "graph_chain": roof(ms_chain),
+                              "eager_python_loop": roof(ms_eager * G / k_eager), "graph_chain": roof(ms_chain),
                               "graph_chain_grid_ordered": roof(ms_chain_g)},
             "roofline_single_chain": roof(ms_chain),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras}

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--dr", default="uniform")
     ap.add_argument("--policy", default="survive")
     ap.add_argument("--warm", type=int, default=30, help="env-steps before the measured launches (mix of episode ages)")
+    ap.add_argument("--lean", action="store_true", help="the 54-byte step (uint16 TimeLimit counter, no reward store)")
+    ap.add_argument("--tile-ordering", default="auto", choices=["auto", "on", "off"])
     a = ap.parse_args()
     if a.kernel == "sample":
         s = renv.TaskSampler("RandomHumanoid-v0")
@@ -38,7 +40,9 @@ def main():
             s.sample_tasks_tensor(a.n, out=buf)
         torch.cuda.synchronize()
         return
-    env = renv.RandomCartPoleVecEnv(a.n, dtype=a.dtype, seed=0, track_truncated=False, track_episodes=False)
+    tile = {"auto": "auto", "on": True, "off": False}[a.tile_ordering]
+    env = renv.RandomCartPoleVecEnv(a.n, dtype=a.dtype, seed=0, track_truncated=False, track_episodes=False, lean=a.lean,
+                                    tile_ordering=tile)
     env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True); env.reset()
     if a.kernel == "step":
         act = env.sample_actions().clone()
@@ -50,7 +54,7 @@ def main():
             env.step(act)
         e1.record(); torch.cuda.synchronize()
         us = 1e3 * e0.elapsed_time(e1) / a.iters
-        b = 62 if a.dtype == "float32" else 114
+        b = (54 if a.lean else 62) if a.dtype == "float32" else 114
         print("step %s n=%d: %.1f us/launch, %.0f GB/s algorithmic" % (a.dtype, a.n, us, b * a.n / us / 1e3))
     else:
         w = (0.1, 0.1, 1.0, 0.3) if a.policy == "survive" else (0.0, 0.0, 1.0, 0.0)
