@@ -759,6 +759,10 @@ __global__ void __launch_bounds__(kSampleThreads) dr_sample_kernel(T *__restrict
 //   * the transforms run on packed pairs (renv_dr.cuh: FFMA2 / FMUL2, the same rounding lane for lane);
 //   * attempt 0 only answers "did any dim fall below its floor" (4 FSETP); the retry loop of the reference, with
 //     its per-dim bookkeeping, is out of line.
+#ifndef RENV_SAMPLER_ILP
+#define RENV_SAMPLER_ILP 2
+#endif
+constexpr int kSamplerIlp = RENV_SAMPLER_ILP;
 #ifndef RENV_SAMPLER_F32_CTAS
 #define RENV_SAMPLER_F32_CTAS 2      // 90-94 registers: round keys, packed constants and parameters all stay resident
 #endif
@@ -808,16 +812,31 @@ dr_sample_f32_kernel(float *__restrict__ out, int64_t n, const __grid_constant__
         // constant words of the segment's counters: (id hi | tick hi, tick lo, purpose | slot)
         const uint32_t c1 = (uint32_t)(id >> 32) & 0xffffu, c2 = call, c3 = ((uint32_t)kTasks << 24) | (uint32_t)j;
         uint32_t c0 = (uint32_t)id;
-#pragma unroll 1
-        for (int k = seg; k > 0; --k) {
-            const uint4 r = philox4x32_10(make_uint4(c0, c1, c2, c3), ks);
+        auto one_block = [&](uint32_t ctr0, float *dst) {
+            const uint4 r = philox4x32_10(make_uint4(ctr0, c1, c2, c3), ks);
             float v[4];
             if (first_attempt_packed<kDrType>(r, pb, v)) {         // rare
-                const RedoneBlock b = sampler_redo_block<kDrType>(&cfg, seed, (id & ~0xffffffffull) | c0, call, j);
+                const RedoneBlock b = sampler_redo_block<kDrType>(&cfg, seed, (id & ~0xffffffffull) | ctr0, call, j);
                 v[0] = b.v0; v[1] = b.v1; v[2] = b.v2; v[3] = b.v3;
                 viol += b.viol;
             }
-            store_block<float, kStore>(row, v, pb.valid);
+            store_block<float, kStore>(dst, v, pb.valid);
+        };
+        int k = seg;
+        if (kSamplerIlp == 2 && kDrType != kDrUniform) {
+            // the transcendental laws are LATENCY-bound (ncu: `wait` 31-36 % of stalls at 2 CTAs/SM: one serial Philox +
+            // Horner chain per thread): two samples per iteration give the scheduler two independent chains
+#pragma unroll 1
+            for (; k >= 2; k -= 2) {
+                one_block(c0, row);
+                one_block(c0 + (uint32_t)samples_per_pass, row + row_step);
+                c0 += 2u * (uint32_t)samples_per_pass;
+                row += 2 * row_step;
+            }
+        }
+#pragma unroll 1
+        for (; k > 0; --k) {
+            one_block(c0, row);
             c0 += (uint32_t)samples_per_pass;
             row += row_step;
         }
