@@ -42,6 +42,11 @@ def test_step_kernel_uses_128_bit_accesses_and_programmatic_dependent_launch(sas
     assert sum(o.startswith("LDG.E.128") for o in ops) >= 9        # 4 state rows + 4 xi rows + elapsed
     assert sum(o.startswith("STG.E.128") for o in ops) >= 6        # 4 state rows + elapsed + reward
     assert "ACQBULK" in ops and "PREEXIT" in ops                   # griddepcontrol.wait / launch_dependents
+    # tile-granular step ordering: ticket atomic, acquire poll, release store, L2 bulk prefetch of the tile
+    assert any(o.startswith("ATOMG.E.ADD.STRONG.GPU") for o in ops) and any(o.startswith("LDG.E.STRONG.GPU") for o in ops)
+    assert any(o.startswith("STG.E.STRONG.GPU") for o in ops) and sum(o.startswith("UBLKPF") for o in ops) >= 4
+    lean = _ops(_one(sass, "cartpole_step_kernelIfLb1ELb0ELb1"))   # lean step: 64-bit load / store of four uint16 counters
+    assert any(o.startswith("LDG.E.64") for o in lean) and any(o.startswith("STG.E.64") for o in lean)
     ops64 = _ops(_one(sass, "cartpole_step_kernelIdLb1ELb0ELb0"))
     assert sum(o.startswith("LDG.E.128") for o in ops64) >= 10 and any(o.startswith("DFMA") for o in ops64)
 
