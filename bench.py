@@ -497,10 +497,24 @@ def run_extras(args, torch, dist, renv, _device, _lib, dev, rank, world, timed, 
     a = lean[0].sample_actions().clone()
     for i in range(40):
         lean[i % 4].step(a)
-    ms = timed(lambda: [lean[i % 4].step(a) for i in range(800)])
+    ms_eager = timed(lambda: [lean[i % 4].step(a) for i in range(800)])
+    # the same 4 x 2^20 envs as ONE single-stream CUDA graph of 400 steps (the eager loop above is partly bound by the
+    # Python launch path at 11 us per call)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for i in range(400):
+                lean[i % 4].step(a)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay(); torch.cuda.synchronize()
+    ms = min(timed(g.replay) for _ in range(5)) * 2.0        # per 800 steps, as the eager figure
+    del g
     gbs = 54 * n * 800 / (ms * 1e-3) / 1e9
     out["step_lean_f32_1M_x4_one_stream"] = {"env_steps_per_s": agg(n * 800, ms), "launch_us": 1e3 * ms / 800, "gbs_per_gpu": gbs,
                                              "frac_of_hbm_peak": gbs / peak, "bytes_per_env_step": 54,
+                                             "eager_env_steps_per_s": agg(n * 800, ms_eager),
                                              "traffic": (json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
                                                          .get("cartpole_step_lean_float32_1M"))}
     del lean, a
