@@ -390,6 +390,7 @@ def test_resident_scalar_env_equals_the_launch_per_step_path_and_sample_task(mon
         a, b = run(True, dr_type, distr, noisy), run(False, dr_type, distr, noisy)
         assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)), dr_type
     monkeypatch.setenv("RENV_SCALAR_RESIDENT", "1")
+    monkeypatch.setenv("RENV_SCALAR_LEASE_US", "300")
     e1, e2 = random_envs.RandomCartPoleEnv(), random_envs.RandomCartPoleEnv()
     for e in (e1, e2):
         e.seed(9); e.set_dr_distribution("uniform", SEARCH); e.set_dr_training(True)
