@@ -154,7 +154,7 @@ bool launch_fullgaussian_tc(float *out, int64_t n, const FullGaussCfg<float> &g,
         gt.mean[k] = 0.25f * g.mean[k];
     }
     const PhiloxKeys ks = philox_keys((uint32_t)seed, (uint32_t)(seed >> 32));
-    dr_sample_fullgaussian_tc_kernel<<<(unsigned)grid, kFgThreads, 0, st>>>(out, n, gt, ks, sample_id0, call, counters);
+    dr_sample_fullgaussian_tc_kernel<<<(unsigned)grid, kFgThreads, kFgPadSmem, st>>>(out, n, gt, ks, sample_id0, call, counters);
     *rc = launch_status();
     return true;
 }

@@ -44,9 +44,16 @@ constexpr uint32_t kFgColZhi = 0, kFgColZlo = 32, kFgColD = 64;
 #ifndef RENV_FG_EXP_NOGEN
 #define RENV_FG_EXP_NOGEN 0
 #endif
-#ifndef RENV_FG_TC_CTAS
-#define RENV_FG_TC_CTAS 4
+#ifndef RENV_FG_TC_SINGLE_D
+#define RENV_FG_TC_SINGLE_D 0       // 1: ONE accumulator, TMEM taken as 64 (Z) + 32 (D) columns -> 5 CTAs per SM; measured 0.928 vs
+                                    //    0.939 ms for 2^24 x 30 (+1 %): occupancy is not what holds the kernel back, left off
 #endif
+#ifndef RENV_FG_TC_CTAS
+#define RENV_FG_TC_CTAS (RENV_FG_TC_SINGLE_D ? 5 : 4)
+#endif
+// SINGLE_D: with two allocations per CTA a sixth resident CTA could take 64 columns and then wait for ever-busy 32;
+// the launcher pads the dynamic shared memory so that exactly five CTAs fit an SM.
+constexpr int kFgPadSmem = RENV_FG_TC_SINGLE_D ? 14848 : 0;
 
 struct __align__(128) FgTcSmem {
     float b_hi[32 * 32];                // F as the B operand, K-major core-matrix layout (see fg_b_index)
@@ -54,6 +61,7 @@ struct __align__(128) FgTcSmem {
     float stage[kFgTile * 32];          // per lane quadrant: 32 rows of `dim` values, contiguous
     unsigned long long mbar;
     uint32_t tmem_base;
+    uint32_t tmem_base_d;               // SINGLE_D: the accumulator's own 32-column allocation
     uint32_t failed;
 };
 
@@ -137,8 +145,15 @@ dr_sample_fullgaussian_tc_kernel(float *__restrict__ out, int64_t n, const __gri
         sm.failed = 0;
     }
     if (warp == 0) {
+#if RENV_FG_TC_SINGLE_D
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&sm.tmem_base)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&sm.tmem_base_d)) : "memory");
+#else
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"((uint32_t)__cvta_generic_to_shared(&sm.tmem_base)), "n"(kFgTmemCols) : "memory");
+#endif
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // B was written through the generic proxy
@@ -146,8 +161,14 @@ dr_sample_fullgaussian_tc_kernel(float *__restrict__ out, int64_t n, const __gri
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmem_base;
+#if RENV_FG_TC_SINGLE_D
+    const uint32_t tmem_d = sm.tmem_base_d;                                // one accumulator, its own allocation
+#else
+    const uint32_t tmem_d = tmem + kFgColD;                                // two accumulators behind Z
+#endif
     const int quad = warp & 3, half = warp >> 2;                           // TMEM lane quadrant / which 16 of the 32 k, d
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);       // this warp's 32 TMEM lanes
+    const uint32_t lane_base_d = tmem_d + ((uint32_t)(quad * 32) << 16);
     const uint64_t desc_hi = fg_smem_desc(sm.b_hi), desc_lo = fg_smem_desc(sm.b_lo);
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&sm.mbar);
 
@@ -162,8 +183,8 @@ dr_sample_fullgaussian_tc_kernel(float *__restrict__ out, int64_t n, const __gri
     // rows of tile `tile` out of accumulator `buf`: clip, denormalise, and write the quadrant's 32 rows as one span
     auto epilogue = [&](int64_t tile, int buf) {
         float x[kFgPer];
-        if (kFgSplit == 1) fg_tmem_ld32(lane_base + kFgColD + 32 * buf, x);
-        else fg_tmem_ld16(lane_base + kFgColD + 32 * buf + 16 * half, x);
+        if (kFgSplit == 1) fg_tmem_ld32(lane_base_d + 32 * buf, x);
+        else fg_tmem_ld16(lane_base_d + 32 * buf + 16 * half, x);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         float *rows = sm.stage + quad * 32 * 32;
         float *row = rows + lane * dim + kFgPer * half;
@@ -217,7 +238,9 @@ dr_sample_fullgaussian_tc_kernel(float *__restrict__ out, int64_t n, const __gri
         }
         // the previous tile's MMAs must have read Z before it is overwritten (they finished long ago: they ran while
         // the normals above were drawn); its accumulator is then ready for the epilogue further down
+#if !RENV_FG_TC_SINGLE_D
         if (it > 0) wait_mma((uint32_t)(it - 1) & 1u);
+#endif
 #pragma unroll
         for (int q = 0; q < kFgPer; q += 8) {
             fg_tmem_st8(lane_base + kFgColZhi + kFgPer * half + q, hi + q);
@@ -230,7 +253,7 @@ dr_sample_fullgaussian_tc_kernel(float *__restrict__ out, int64_t n, const __gri
         // ---- 2. D[it & 1] = Z F^T on the tensor core
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d_col = tmem + kFgColD + 32 * (it & 1);
+            const uint32_t d_col = RENV_FG_TC_SINGLE_D ? tmem_d : tmem_d + 32 * (it & 1);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {               // K-step s: columns 8 s .. 8 s + 7 of Z, 256 bytes further into B
                 const uint64_t off = (uint64_t)((256u * s) >> 4);
@@ -245,21 +268,35 @@ dr_sample_fullgaussian_tc_kernel(float *__restrict__ out, int64_t n, const __gri
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
         }
 
+#if RENV_FG_TC_SINGLE_D
+        // ---- 3. wait for this tile's MMAs (the other four CTAs of the SM fill the gap), then its epilogue
+        wait_mma((uint32_t)it & 1u);
+        epilogue(tile, 0);
+#else
         // ---- 3. epilogue of the PREVIOUS tile while the tensor core works on this one
         if (it > 0) epilogue(prev_tile, (it - 1) & 1);
         prev_tile = tile;
+#endif
     }
+#if !RENV_FG_TC_SINGLE_D
     if (it > 0) {
         wait_mma((uint32_t)(it - 1) & 1u);
         epilogue(prev_tile, (it - 1) & 1);
     }
+#endif
 
     // ---- teardown
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0 && sm.failed && counters) atomicAdd(counters + kCounterOrderTimeout, 1ull);
-    if (warp == 0)
+    if (warp == 0) {
+#if RENV_FG_TC_SINGLE_D
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" :: "r"(tmem) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" :: "r"(tmem_d) : "memory");
+#else
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(kFgTmemCols) : "memory");
+#endif
+    }
 }
 
 }  // namespace renv
