@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=6)
     ap.add_argument("--K", type=int, default=500)
     ap.add_argument("--dr", default="uniform")
-    ap.add_argument("--policy", default="survive")
+    ap.add_argument("--policy", default="survive", choices=["survive", "resetheavy", "random"])
     ap.add_argument("--warm", type=int, default=30, help="env-steps before the measured launches (mix of episode ages)")
     ap.add_argument("--lean", action="store_true", help="the 54-byte step (uint16 TimeLimit counter, no reward store)")
     ap.add_argument("--tile-ordering", default="auto", choices=["auto", "on", "off"])
@@ -57,7 +57,7 @@ def main():
         b = (54 if a.lean else 62) if a.dtype == "float32" else 114
         print("step %s n=%d: %.1f us/launch, %.0f GB/s algorithmic" % (a.dtype, a.n, us, b * a.n / us / 1e3))
     else:
-        w = (0.1, 0.1, 1.0, 0.3) if a.policy == "survive" else (0.0, 0.0, 1.0, 0.0)
+        w = {"survive": (0.1, 0.1, 1.0, 0.3), "resetheavy": (0.0, 0.0, 1.0, 0.0), "random": None}[a.policy]
         for _ in range(a.iters):
             env.rollout(w, 0.0, a.K)
         torch.cuda.synchronize()

@@ -54,10 +54,13 @@ def main():
     ap.add_argument("--K", type=int, default=500)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-dr", action="store_true")
+    ap.add_argument("--only", default="")
     a = ap.parse_args()
     n = 1 << a.log2n
     out = {"lib": os.environ.get("RENV_B200_LIB", "default"), "n": n, "K": a.K}
     for name, w in (("survive", [0.1, 0.1, 1.0, 0.3]), ("resetheavy", [0.0, 0.0, 1.0, 0.0]), ("random", None)):
+        if a.only and name not in a.only.split(","):
+            continue
         out[name] = run(n, a.K, w, not a.no_dr, a.reps)
     print(json.dumps(out))
 

@@ -477,13 +477,13 @@ template <typename T> struct RolloutThread {
     int32_t el; uint32_t new_episodes; bool xi_dirty;
     int remaining;      // steps this lane may still execute now (0 while parked or finished)
     int parked;         // steps left after the pending reset, -1 when not parked
-    uint64_t reset_tick;
     // Noisy variant only: the observation the policy sees at the next step.  Either the one found in the obs buffer
     // at launch (obs_loaded), or state + std * N(0,I) keyed by the tick that produced the state and `after_reset`
     // (0: a step's observation, 1: a reset's) -- exactly what step() / reset() wrote for that tick.
     State<T> obs0; bool obs_loaded; uint32_t after_reset;
     unsigned long long sum_r2; unsigned sum_r; float min_r, max_r; unsigned episodes, sum_len, viol;
     ActionBits act;     // random policy only: the env's current 128 action bits
+    bool refresh;       // ... and: parked for new action bits only, the episode goes on
 };
 
 #ifndef RENV_RESET_BATCH
@@ -509,27 +509,21 @@ constexpr int kUnrollF64 = RENV_UNROLL_F64;
 // re-derived a whole block for one bit, and the random-policy rollout ran at 0.11 of the FMA peak).
 __device__ __forceinline__ uint32_t action_bit(const uint4 &r, uint32_t step)
 {
-    const uint32_t sel = (step >> 5) & 3u;
-    const uint32_t word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
-    return (word >> (step & 31u)) & 1u;
+    // bit (step & 127) of the 128-bit block x | y << 32 | z << 64 | w << 96, without a branch: two selects pick the
+    // 64-bit half, one 64-bit shift the bit (a 4-way word select compiled to a divergent branch tree, ~12 issue slots)
+    const bool hi = (step & 64u) != 0u;
+    const uint64_t half = (uint64_t)(hi ? r.w : r.y) << 32 | (uint64_t)(hi ? r.z : r.x);
+    return (uint32_t)(half >> (step & 63u)) & 1u;
 }
-__device__ __forceinline__ int random_action(ActionBits &c, uint64_t seed, uint64_t id, uint64_t tick)
-{
-    const uint32_t step = (uint32_t)tick;
-    if ((step >> 7) != c.group) {
-        c.group = step >> 7;
-        c.r = draw_block(seed, id, (uint64_t)c.group, kAction, 0);
-    }
-    return (int)action_bit(c.r, step);
-}
-
 template <typename T, bool kEuler, bool kKnownSmall, bool kNoisy = false, bool kRandom = false>
 __device__ __forceinline__ void rollout_step(RolloutThread<T> &t, const RolloutArgs<T> &a, const Policy<T> &policy,
                                              int32_t limit, uint64_t id = 0)
 {
     int action;
+    uint32_t step = 0u;
     if (kRandom) {      // action_space.sample() of the reference's demo loop (test_random_policy.py:26), per env and tick
-        action = random_action(t.act, a.env.seed, id, a.tick + (uint64_t)(a.K - t.remaining));
+        step = (uint32_t)a.tick + (uint32_t)(a.K - t.remaining);
+        action = (int)action_bit(t.act.r, step);        // t.act always holds the block of step >> 7 (see below)
     } else if (kNoisy) {       // the policy acts on the OBSERVATION of the current state (what step()/reset() returned for it)
         State<T> o = t.obs0;
         if (!t.obs_loaded) {
@@ -545,30 +539,52 @@ __device__ __forceinline__ void rollout_step(RolloutThread<T> &t, const RolloutA
     }
     const bool terminated = dynamics<kKnownSmall>(t.s, t.p, t.d, action, kEuler);
     t.el += 1;
-    if (terminated || t.el >= limit) {
-        const float ret = (float)t.el;
-        t.episodes += 1; t.sum_len += (unsigned)t.el;
-        t.sum_r += (unsigned)t.el; t.sum_r2 += (unsigned long long)t.el * (unsigned)t.el;   // integers: reward is 1.0/step
-        t.min_r = fminf(t.min_r, ret); t.max_r = fmaxf(t.max_r, ret);
-        t.new_episodes += 1; t.el = 0;
-        t.reset_tick = a.tick + (uint64_t)(a.K - t.remaining);     // the clock value a single step() would use
-        t.parked = t.remaining - 1;
-        t.remaining = 1;                                           // becomes 0 below: the lane sits out
+    // End of episode: two selects, no branch (some lane of the warp ends an episode on most steps of a short-episode
+    // policy, so a branch here is taken by nearly every warp).  The lane sits out with t.el = the episode's length;
+    // statistics and the reset itself happen in rollout_reset.
+    const bool ended = terminated || t.el >= limit;
+    bool park = ended;
+    if (kRandom) {
+        // The env's 128 action bits run out after this step: the lane parks like one whose episode ended and gets the
+        // next block in the warp's reset pass, together with the other parked lanes, instead of running Philox alone
+        // inside the step loop (22 % of the warp-steps had such a lane: 10 issue slots per step).
+        const bool cross = ((step + 1u) & 127u) == 0u;
+        t.refresh = cross && !ended;
+        park = ended || cross;
     }
-    t.remaining -= 1;
+    t.parked = park ? t.remaining - 1 : t.parked;
+    t.remaining = park ? 0 : t.remaining - 1;
 }
 
-template <typename T>
+template <typename T, bool kRandom = false>
 __device__ __forceinline__ void rollout_reset(RolloutThread<T> &t, const RolloutArgs<T> &a, uint64_t id)
 {
-    if (a.dr.dr_type != kDrNone) {
-        t.p = Xi<T>{ T(0), T(0), T(0), T(0) };
-        t.viol += sample_xi(t.p, a.dr, a.env.seed, id, t.reset_tick);
-        t.d = derive(t.p);
-        t.xi_dirty = true;
+    if (!(kRandom && t.refresh)) {
+        // the episode that just ended (return == length: the reward is 1.0 on every step, :207-212)
+        const float ret = (float)t.el;
+        t.episodes += 1; t.sum_len += (unsigned)t.el;
+        t.sum_r += (unsigned)t.el; t.sum_r2 += (unsigned long long)t.el * (unsigned)t.el;
+        t.min_r = fminf(t.min_r, ret); t.max_r = fmaxf(t.max_r, ret);
+        t.new_episodes += 1; t.el = 0;
+        // the clock value a single step() would have used for the step that ended it: t.parked steps were left after it
+        const uint64_t reset_tick = a.tick + (uint64_t)(a.K - t.parked - 1);
+        if (a.dr.dr_type != kDrNone) {
+            t.p = Xi<T>{ T(0), T(0), T(0), T(0) };
+            t.viol += sample_xi(t.p, a.dr, a.env.seed, id, reset_tick);
+            t.d = derive(t.p);
+            t.xi_dirty = true;
+        }
+        init_state(t.s, a.env.seed, id, reset_tick);
+        t.after_reset = 1u;
     }
-    init_state(t.s, a.env.seed, id, t.reset_tick);
-    t.after_reset = 1u;
+    if (kRandom) {      // the action bits of the step the lane resumes at
+        const uint32_t group = ((uint32_t)a.tick + (uint32_t)(a.K - t.parked)) >> 7;
+        if (group != t.act.group) {
+            t.act.group = group;
+            t.act.r = draw_block(a.env.seed, id, (uint64_t)group, kAction, 0);
+        }
+        t.refresh = false;
+    }
     t.remaining = t.parked;
     t.parked = -1;
 }
@@ -596,9 +612,10 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
     t.p = load_xi(a.env.xi, il);
     t.d = derive(t.p);
     t.el = a.env.elapsed[il];
-    t.new_episodes = 0; t.xi_dirty = false; t.parked = -1; t.reset_tick = 0;
+    t.new_episodes = 0; t.xi_dirty = false; t.parked = -1;
     t.obs_loaded = kNoisy; t.after_reset = 0u;
-    t.act.group = 0xffffffffu; t.act.r = make_uint4(0, 0, 0, 0);
+    t.act.group = (uint32_t)a.tick >> 7; t.act.r = make_uint4(0, 0, 0, 0); t.refresh = false;
+    if (kRandom) t.act.r = draw_block(a.env.seed, a.env.env_id0 + (uint64_t)il, (uint64_t)t.act.group, kAction, 0);
     if (kNoisy) t.obs0 = State<T>{ a.env.obs[il], a.env.obs[ld + il], a.env.obs[2 * ld + il], a.env.obs[3 * ld + il] };
     else t.obs0 = t.s;
     const uint64_t id = a.env.env_id0 + (uint64_t)il;
@@ -622,7 +639,7 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
         const unsigned parked = __ballot_sync(0xffffffffu, t.parked >= 0);
         const unsigned running = __ballot_sync(0xffffffffu, t.remaining > 0);
         if (parked != 0u && (__popc(parked) >= kResetBatch || running == 0u)) {
-            if (t.parked >= 0) rollout_reset(t, a, id);
+            if (t.parked >= 0) rollout_reset<T, kRandom>(t, a, id);
             continue;                       // revived lanes may still have steps to do
         }
         if (running == 0u) break;           // nobody parked, nobody running
