@@ -282,7 +282,7 @@ int cartpole_step(const renv_cartpole_env *env, const renv_obs_noise *noise, con
 }
 
 // Random policy (w == NULL): one env per thread for both element types (an env draws one Philox block per 128 env-steps
-// for its action bits).  The fp32 env-PAIR kernel was tried for it and is slower (1.4e11 vs 2.4e11 env-steps/s): with
+// for its action bits).  The fp32 env-PAIR kernel was tried for it and is slower (1.4e11 vs 2.4e11 env-steps/s at the time, 3.2e11 now): with
 // ~27-step episodes a pair spends most packed steps with one slot parked for its reset.
 template <typename T> int launch_rollout_random(const RolloutArgs<T> &a, cudaStream_t stream)
 {

@@ -498,6 +498,19 @@ template <typename T> struct RolloutThread {
 constexpr int kResetBatch = RENV_RESET_BATCH;          // parked lanes per warp that trigger a reset pass
 constexpr int kStepsPerCheck = RENV_STEPS_PER_CHECK;   // env-steps between two warp votes
 constexpr int kUnrollF64 = RENV_UNROLL_F64;
+// The fp32 random policy ends an episode every ~25 steps: its own vote period / batch size / unroll.  Measured at
+// 2^24 envs x 500 steps (check, batch -> 1e11 env-steps/s): (4,4) 2.48, (8,4) 2.92, (12,4) 3.05, (16,8) 3.11,
+// (16,12) 3.08, (20,12) 3.06, (24,12) 2.95, (32,16) 2.61; unroll 1 / 2 / 4 / 8 at (8,4): 2.79 / 2.92 / 2.81 / 2.75.
+#ifndef RENV_RANDOM_RESET_BATCH
+#define RENV_RANDOM_RESET_BATCH 8
+#endif
+#ifndef RENV_RANDOM_STEPS_PER_CHECK
+#define RENV_RANDOM_STEPS_PER_CHECK 16
+#endif
+#ifndef RENV_RANDOM_UNROLL
+#define RENV_RANDOM_UNROLL RENV_UNROLL_F64
+#endif
+constexpr int kRandomUnroll = RENV_RANDOM_UNROLL;
 #ifndef RENV_ROLLOUT_F64_CTAS
 #define RENV_ROLLOUT_F64_CTAS 3
 #endif
@@ -631,6 +644,10 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 #pragma unroll
             for (int u = 0; u < kStepsPerCheck; ++u)
                 if (t.remaining > 0) rollout_step<T, kEuler, true, kNoisy, kRandom>(t, a, policy, limit, id);
+        } else if (kRandom && sizeof(T) == 4) {
+#pragma unroll kRandomUnroll
+            for (int u = 0; u < RENV_RANDOM_STEPS_PER_CHECK; ++u)
+                if (t.remaining > 0) rollout_step<T, kEuler, true, kNoisy, kRandom>(t, a, policy, limit, id);
         } else {            // the fp64 / noisy step is ~10x the code of the fp32 one: keep the loop body inside the i-cache
 #pragma unroll kUnrollF64
             for (int u = 0; u < kStepsPerCheck; ++u)
@@ -638,7 +655,7 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
         }
         const unsigned parked = __ballot_sync(0xffffffffu, t.parked >= 0);
         const unsigned running = __ballot_sync(0xffffffffu, t.remaining > 0);
-        if (parked != 0u && (__popc(parked) >= kResetBatch || running == 0u)) {
+        if (parked != 0u && (__popc(parked) >= (kRandom && sizeof(T) == 4 ? RENV_RANDOM_RESET_BATCH : kResetBatch) || running == 0u)) {
             if (t.parked >= 0) rollout_reset<T, kRandom>(t, a, id);
             continue;                       // revived lanes may still have steps to do
         }
