@@ -412,7 +412,8 @@ def run_b200(args):
                     "profiles/r1/pcie_aggregate_8gpu.txt)" % (e2e_value / world * d2h_bytes / n / 1e9,
                                                              e2e_value * d2h_bytes / n / 1e9),
            "api": "RandomCartPoleVecEnv.step_host_async(numpy uint8 actions) / step_host_wait() -> numpy obs, reward, "
-                  "done; %d env batches round-robin, one step in flight per batch; obs + done cross PCIe, the reward "
+                  "done; %d env batches round-robin, one step in flight per batch; obs + done cross PCIe (done as bits: packed on "
+                  "the device by renv_pack_flags_u8, unpacked into the numpy bool array inside step_host_wait), the reward "
                   "(identically 1.0 under auto-reset, random_cartpole.py:207-212) is a constant host array" % R}
 
     extras = {}

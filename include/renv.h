@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RENV_ABI_VERSION 5
+#define RENV_ABI_VERSION 6
 #define RENV_MAX_DIM 32          /* largest task_dim in the suite is 30 (jinja/random_humanoid.py) */
 #define RENV_NUM_STATS 6         /* episodes, sum R, sum R^2, min R, max R, sum length */
 #define RENV_TILE_ENVS_F32 1024  /* envs per step CTA: the granule of renv_cartpole_env.progress */
@@ -240,6 +240,12 @@ int renv_cartpole_scalar_serve(renv_scalar_ctrl *ctrl, void *save, uint32_t leas
  * Philox block (e, step >> 7), purpose 2 -- one block holds an env's Bernoulli(1/2) actions for 128 consecutive steps. */
 int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_t seed, uint32_t step,
                            void *stream);
+
+/* Host-path helper (no counterpart in the reference, whose envs live in host memory): packs n byte flags (0 / non-zero,
+ * the `done` / `truncated` vectors of renv_cartpole_step_*) into bits -- bit (i & 7) of byte i >> 3, numpy's
+ * bitorder "little" -- so that they cross PCIe as n / 8 bytes.  `bits` holds ceil(n / 32) 32-bit words; both pointers
+ * 4-byte aligned (16-byte aligned flags take the vector path). */
+int renv_pack_flags_u8(const uint8_t *flags, uint32_t *bits, int64_t n, void *stream);
 
 #ifdef __cplusplus
 }

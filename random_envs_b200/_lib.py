@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RENV_B200_LIB", os.path.join(_HERE, "librenv_b200.so"))   # override: kernel experiments
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_DIM = 32
 NUM_STATS = 6
 SCALAR_SAVE_BYTES = 512     # RENV_SCALAR_SAVE_BYTES
@@ -70,6 +70,7 @@ SIGNATURES = {
     "renv_cartpole_rollout_noisy_f64": (_int, [_env_p, _noise_p, ctypes.POINTER(_dbl), _dbl, _int, _int, _int, _u64, _cfg_p, _vp, _vp, _vp]),
     "renv_cartpole_scalar_serve": (_int, [_vp, _vp, _u32, _u64, _vp]),
     "renv_random_actions_u8": (_int, [_vp, _i64, _u64, _u64, _u32, _vp]),
+    "renv_pack_flags_u8": (_int, [_vp, _vp, _i64, _vp]),
 }
 
 

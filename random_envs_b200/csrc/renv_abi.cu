@@ -503,4 +503,16 @@ int renv_random_actions_u8(uint8_t *action, int64_t n, uint64_t env_id0, uint64_
     return launch_status();
 }
 
+int renv_pack_flags_u8(const uint8_t *flags, uint32_t *bits, int64_t n, void *stream)
+{
+    if (flags == nullptr || bits == nullptr) return RENV_E_NULL;
+    if (n <= 0) return RENV_E_SIZE;
+    if (!aligned(flags, 4) || !aligned(bits, 4)) return RENV_E_ALIGN;
+    const int64_t threads = (n + 31) / 32;
+    const int64_t blocks = (threads + 255) / 256;
+    if (blocks > 0x7fffffffLL) return RENV_E_SIZE;
+    pack_flags_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(flags, bits, n);
+    return launch_status();
+}
+
 }  // extern "C"

@@ -678,6 +678,34 @@ cartpole_rollout_kernel(const __grid_constant__ RolloutArgs<T> a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Host path: done / truncated flags cross PCIe as bits (n / 8 bytes instead of n)
+// ------------------------------------------------------------------------------------------------
+// 4 flag bytes -> 4 bits (bit k set when byte k != 0)
+__device__ __forceinline__ uint32_t nibble_of(uint32_t v)
+{
+    return ((__vcmpne4(v, 0u) & 0x08040201u) * 0x01010101u) >> 24;
+}
+// Thread w packs flags[32 w .. 32 w + 31] into bits[w]: bit (i & 31) of word i >> 5, i.e. bit (i & 7) of byte i >> 3
+// (numpy's bitorder="little").  Flags past n count as 0.
+__global__ void __launch_bounds__(256)
+pack_flags_kernel(const uint8_t *__restrict__ flags, uint32_t *__restrict__ bits, int64_t n)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = w * 32;
+    if (i0 >= n) return;
+    uint32_t out = 0u;
+    if (i0 + 32 <= n && (reinterpret_cast<uintptr_t>(flags) & 15u) == 0u) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(flags + i0));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(flags + i0) + 1);
+        out = nibble_of(a.x) | nibble_of(a.y) << 4 | nibble_of(a.z) << 8 | nibble_of(a.w) << 12 |
+              nibble_of(b.x) << 16 | nibble_of(b.y) << 20 | nibble_of(b.z) << 24 | nibble_of(b.w) << 28;
+    } else {
+        for (int k = 0; k < 32 && i0 + k < n; ++k) out |= (flags[i0 + k] != 0 ? 1u : 0u) << k;
+    }
+    bits[w] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
 // RandomEnv.sample_tasks(n) -> (n, dim) row-major, dim <= 32
 // ------------------------------------------------------------------------------------------------
 constexpr int kSampleThreads = 256;

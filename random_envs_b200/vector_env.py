@@ -46,11 +46,13 @@ class RandomCartPoleVecEnv(RandomEnv):
     def __init__(self, num_envs, dtype="float32", device=None, seed=0, env_id0=0,
                  max_episode_steps=MAX_EPISODE_STEPS, auto_reset=True, kinematics_integrator="euler",
                  track_truncated=True, validate_actions=True, track_episodes=True, noisy=False, noise_level=1e-4,
-                 lean=False, tile_ordering="auto"):
+                 lean=False, tile_ordering="auto", pack_host_flags=True):
         RandomEnv.__init__(self)
         if num_envs <= 0:
             raise ValueError("num_envs must be positive")
         self.num_envs = int(num_envs)
+        # step_host_*: done / truncated cross PCIe as bits (renv_pack_flags_u8) and are unpacked on the host
+        self.pack_host_flags = bool(pack_host_flags)
         self._dtype_name = str(dtype).replace("torch.", "")
         if self._dtype_name not in ("float32", "float64"):
             raise ValueError("dtype must be float32 or float64")
@@ -430,6 +432,11 @@ class RandomCartPoleVecEnv(RandomEnv):
                      done=t.empty(b["ld"], dtype=t.uint8).pin_memory(),
                      truncated=t.empty(b["ld"], dtype=t.uint8).pin_memory(),
                      counters=t.zeros(_lib.NUM_COUNTERS, dtype=t.int64).pin_memory())
+            # flag bits: [0] done, [1] truncated, ceil(ld / 32) words each (device twin in b["flag_bits"])
+            words = (b["ld"] + 31) // 32
+            h["flag_bits"] = t.zeros((2, words), dtype=t.int32).pin_memory()
+            b["flag_bits"] = t.zeros((2, words), dtype=t.int32, device=b["device"])
+            h["flag_bytes"] = h["flag_bits"].numpy().view(np.uint8)          # (2, 4 * words)
             h["np"] = dict(action=h["action"].numpy()[:n], obs=h["state"].numpy()[:, :n].T,
                            reward=h["reward"].numpy()[:n], done=h["done"].numpy()[:n].view(np.bool_),
                            truncated=h["truncated"].numpy()[:n].view(np.bool_))
@@ -466,9 +473,19 @@ class RandomCartPoleVecEnv(RandomEnv):
             h["state"].copy_(b["obs"] if self.noisy else b["state"], non_blocking=True)
             if not self.auto_reset:        # only the steps-beyond-done rule (:213-222) ever yields 0.0
                 h["reward"].copy_(b["reward"], non_blocking=True)
-            h["done"].copy_(b["done"], non_blocking=True)
-            if self.track_truncated:
-                h["truncated"].copy_(b["truncated"], non_blocking=True)
+            if self.pack_host_flags:
+                sp = _device.stream_ptr(b["device"])
+                bits = b["flag_bits"]
+                _lib.call("renv_pack_flags_u8", _device.ptr(b["done"]), _device.ptr(bits[0]), self.num_envs, sp)
+                if self.track_truncated:
+                    _lib.call("renv_pack_flags_u8", _device.ptr(b["truncated"]), _device.ptr(bits[1]), self.num_envs, sp)
+                    h["flag_bits"].copy_(bits, non_blocking=True)
+                else:
+                    h["flag_bits"][0].copy_(bits[0], non_blocking=True)
+            else:
+                h["done"].copy_(b["done"], non_blocking=True)
+                if self.track_truncated:
+                    h["truncated"].copy_(b["truncated"], non_blocking=True)
             h["counters"].copy_(self._violation_counter(b["device"]), non_blocking=True)    # 16 bytes: the error flags
             h["event"].record(stream)
 
@@ -476,7 +493,8 @@ class RandomCartPoleVecEnv(RandomEnv):
         """(host->device, device->host) bytes one ``step_host`` moves over PCIe."""
         esize = 4 if self._dtype_name == "float32" else 8
         ld = self._alloc()["ld"]
-        d2h = 4 * ld * esize + ld + (0 if self.auto_reset else ld * esize) + (ld if self.track_truncated else 0) \
+        flag = 4 * ((ld + 31) // 32) if self.pack_host_flags else ld
+        d2h = 4 * ld * esize + flag + (0 if self.auto_reset else ld * esize) + (flag if self.track_truncated else 0) \
             + 8 * _lib.NUM_COUNTERS
         return ld, d2h
 
@@ -488,6 +506,11 @@ class RandomCartPoleVecEnv(RandomEnv):
         if int(c[0]) | int(c[1]):          # the device flagged a gaussian failure or an invalid action (see ``step``)
             self.check_dr_violations()
         v = h["np"]
+        if self.pack_host_flags:
+            n = self.num_envs
+            np.copyto(v["done"].view(np.uint8), np.unpackbits(h["flag_bytes"][0], count=n, bitorder="little"))
+            if self.track_truncated:
+                np.copyto(v["truncated"].view(np.uint8), np.unpackbits(h["flag_bytes"][1], count=n, bitorder="little"))
         return v["obs"], v["reward"], v["done"], v["truncated"]
 
     def step_host(self, actions):

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(lib, n), "%s declared in renv.h but not exported" % n
     assert sorted(_lib.SIGNATURES) == names, "ctypes binding and header disagree"
     header_version = int(re.search(r"#define RENV_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
-    assert _lib.load().renv_abi_version() == _lib.ABI_VERSION == header_version == 5
+    assert _lib.load().renv_abi_version() == _lib.ABI_VERSION == header_version == 6
 
 
 def test_header_constants_match_binding():

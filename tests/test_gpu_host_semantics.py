@@ -1,6 +1,8 @@
 """Host-side semantics the round-1 review found missing: DR stream keyed by the constructor seed and the GLOBAL env id
 (shard invariance of set_random_task), re-seeding restarts the episode stream, checkpoints carry the DR state, action
 tensors are checked for device / shape, device-side errors surface at every synchronising call."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -108,3 +110,49 @@ def test_gaussian_failure_surfaces_at_every_synchronising_call():
     with pytest.raises(Exception, match="Not all samples were above"):
         e.check_dr_violations()
     del ok
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4096, 100003])
+def test_pack_flags_matches_numpy_packbits(n):
+    """renv_pack_flags_u8: bit (i & 7) of byte i >> 3 == flags[i] != 0 (numpy bitorder "little"), any n, flags past n
+    ignored, the 16-byte-aligned vector path and the unaligned scalar path."""
+    from random_envs_b200 import _device, _lib
+    rng = np.random.default_rng(n)
+    flags = rng.integers(0, 3, size=n + 4, dtype=np.uint8)          # 0, 1, 2: any non-zero byte is a set flag
+    flags[rng.integers(0, n)] = 255
+    want = np.packbits(flags[:n] != 0, bitorder="little")
+    dev = torch.as_tensor(flags, device="cuda")
+    words = (n + 31) // 32
+    for offset in (0, 4):                                           # offset 4: aligned to 4 only -> scalar path
+        src = dev[offset:offset + n]
+        want_o = np.packbits(flags[offset:offset + n] != 0, bitorder="little")
+        bits = torch.full((words,), -1, dtype=torch.int32, device="cuda")
+        _lib.call("renv_pack_flags_u8", _device.ptr(src), _device.ptr(bits), n, _device.stream_ptr(dev.device))
+        got = bits.cpu().numpy().view(np.uint8)[:len(want_o)]
+        assert np.array_equal(got, want_o)
+        assert np.array_equal(np.unpackbits(got, count=n, bitorder="little"), (flags[offset:offset + n] != 0).astype(np.uint8))
+    assert np.array_equal(np.packbits(flags[:n] != 0, bitorder="little"), want)
+    with pytest.raises(_lib.RenvError):
+        _lib.call("renv_pack_flags_u8", ctypes.c_void_p(dev.data_ptr() + 1), _device.ptr(bits), n,
+                  _device.stream_ptr(dev.device))
+    with pytest.raises(_lib.RenvError):
+        _lib.call("renv_pack_flags_u8", None, _device.ptr(bits), n, _device.stream_ptr(dev.device))
+
+
+@pytest.mark.parametrize("n", [1000, 4097])
+def test_step_host_with_packed_flags_equals_byte_flags(n):
+    """step_host_* moves done / truncated as bits by default; the numpy results equal those of the byte path on every
+    step, including the steps where episodes end (TimeLimit 20 so that `truncated` fires too)."""
+    a = _env(n, seed=11, max_episode_steps=20)
+    b = _env(n, seed=11, max_episode_steps=20, pack_host_flags=False)
+    assert a.host_bytes_per_step()[1] < b.host_bytes_per_step()[1]
+    a.reset(); b.reset()
+    rng = np.random.default_rng(0)
+    ended = truncated = 0
+    for _ in range(60):
+        act = rng.integers(0, 2, size=n, dtype=np.uint8)
+        ra, rb = a.step_host(act), b.step_host(act)
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+        ended += int(ra[2].sum()); truncated += int(ra[3].sum())
+    assert ended > n and truncated > 0
