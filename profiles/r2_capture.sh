@@ -24,4 +24,6 @@ cap sample_f32_gaussian_16M dr_sample 1 python profiles/drive.py sample --n 1677
 cap sample_f32_truncnorm_16M dr_sample 1 python profiles/drive.py sample --n 16777216 --dr truncnorm --iters 3
 cap fullgaussian_tc_4M fullgaussian_tc 1 python profiles/exp/drive_fullgaussian.py
 cap rollout_pair_f32_4M_K100 rollout_pair 0 python profiles/drive.py rollout --n 4194304 --iters 1 --K 100
+cap rollout_pair_resetheavy_4M_K300 rollout_pair 0 python profiles/drive.py rollout --n 4194304 --iters 1 --K 300 --policy resetheavy
+cap rollout_random_f32_4M_K100 cartpole_rollout_kernel 0 python profiles/drive.py rollout --n 4194304 --iters 1 --K 100 --policy random
 ls -la $O
