@@ -351,6 +351,30 @@ def test_random_policy_rollout_equals_step_with_sample_actions(dtype, n, K, limi
         assert 15 < st["mean_return"] < 40                    # random policy over the search bounds: ~27 steps
 
 
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("pre,K", [(125, 1), (126, 1), (126, 2), (127, 1), (127, 130), (120, 300), (254, 4)])
+def test_random_policy_rollout_across_action_block_boundaries(dtype, pre, K):
+    """An env's 128 action bits run out at every multiple of 128 of the step clock; in the fused rollout the lane then
+    parks for the warp's reset pass to fetch the next block.  Start the launch `pre` ticks into the stream so that the
+    boundary falls on its first step, its last step, in the middle, twice, or right after the launch."""
+    n = 777
+    mk = lambda: random_envs.RandomCartPoleVecEnv(n, dtype=dtype, seed=5, env_id0=9000, max_episode_steps=40)
+    fused, stepped = mk(), mk()
+    for e in (fused, stepped):
+        e.set_dr_distribution("uniform", SEARCH); e.set_dr_training(True); e.reset()
+        for _ in range(pre):
+            e.step(e.sample_actions())
+    assert torch.equal(fused.obs, stepped.obs)
+    fused.rollout(None, 0.0, K)
+    for _ in range(K):
+        stepped.step(stepped.sample_actions())
+    assert torch.equal(fused.obs, stepped.obs) and torch.equal(fused.get_task(), stepped.get_task())
+    assert torch.equal(fused.elapsed, stepped.elapsed) and torch.equal(fused.episode, stepped.episode)
+    # and the stream continues identically after the launch (the clock advanced by K)
+    a, b = fused.sample_actions().clone(), stepped.sample_actions().clone()
+    assert torch.equal(a, b)
+
+
 def test_in_place_edits_of_the_distribution_arrays_take_effect():
     """The reference reads min_task / max_task at every draw (random_env.py:151): editing them in place between steps
     changes what the next reset samples, without calling set_dr_distribution again."""
