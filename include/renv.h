@@ -212,7 +212,7 @@ int renv_cartpole_rollout_noisy_f64(const renv_cartpole_env *env, const renv_obs
  * `request = (seq << 8) | op` (seq grows by 1 per request, 24 bits; op 0 / 1 = step(action); 2 = reset, 3 = set state,
  * 4 = set xi, 5 = configure, 6 = exit, each reading the `arg` / `arg_u64` fields that the host wrote BEFORE the request
  * word -- see csrc/renv_scalar_server.cuh for the field meanings) and spins on `ack == seq`; the results are in
- * state / obs / xi / reward / done / beyond / violations.  `save` is RENV_SCALAR_SAVE_BYTES of zero-initialised DEVICE
+ * state / obs / xi / reward / done / beyond / violations (or, for a step, already in `next[action]`, see below).  `save` is RENV_SCALAR_SAVE_BYTES of zero-initialised DEVICE
  * memory that carries the env between kernel instances: the kernel is a lease -- after `lease_ns` without a request it
  * stores its registers there, sets ctrl->exited = lease_id and exits; the caller launches the next instance (lease_id
  * + 1) when it has a request and sees exited == the id it launched last.  One instance at a time per ctrl block. */
@@ -232,7 +232,24 @@ typedef struct renv_scalar_ctrl {
     uint32_t pad1;
     uint32_t ack;                /* device -> host: seq of the last request served */
     uint32_t exited;             /* device -> host: lease id of the instance that has exited */
-    uint32_t pad2[14];
+    uint32_t pad2[16];
+    /* Look-ahead (device -> host; enabled by arg_u64[5] != 0 of a configure request): after serving request `next_seq`
+     * the kernel also publishes what step(0) and step(1) would return from the state it is in now.  A host that finds
+     * next_seq == the seq of its last request takes next[action] as the result of its next step AT ONCE and rings that
+     * step in as op 8 + action WITHOUT waiting (ops 8 / 9 are not acknowledged and write no result block; at most one
+     * request is outstanding: before it rings again the host waits for next_seq == that step's seq), which takes the
+     * PCIe round trip off the step's critical path.  The kernel counts the step clock itself for the Noisy variant's
+     * observations (tick of the last reset + 1 per step, or arg_u64[4] of a configure request). */
+    struct renv_scalar_outcome {
+        double state[4];
+        double obs[4];           /*   Noisy variant */
+        double reward;
+        int32_t done;
+        int32_t beyond;
+        uint32_t pad[12];
+    } next[2];
+    uint32_t next_seq;           /* release-stored after next[0..1] */
+    uint32_t pad3[15];
 } renv_scalar_ctrl;
 int renv_cartpole_scalar_serve(renv_scalar_ctrl *ctrl, void *save, uint32_t lease_id, uint64_t lease_ns, void *stream);
 

@@ -20,6 +20,7 @@ resamples xi -- the reference CartPole forgets to (random_cartpole.py:226-229) a
 env of the suite does.  Pass ``resample_on_reset=False`` to get the reference's literal behaviour.
 """
 import ctypes
+import struct
 import math
 
 import numpy as np
@@ -99,8 +100,9 @@ class _ResidentScalarCore:
 
     # byte offsets of struct renv_scalar_ctrl
     OFF_REQUEST, OFF_ARG, OFF_ARG_U64, OFF_STATE, OFF_OBS, OFF_XI, OFF_REWARD, OFF_DONE, OFF_BEYOND, OFF_VIOL, OFF_ACK, \
-        OFF_EXITED, SIZE = 0, 64, 192, 256, 288, 320, 352, 360, 364, 368, 376, 380, 440
-    OP_RESET, OP_SET_STATE, OP_SET_XI, OP_CONFIG, OP_EXIT = 2, 3, 4, 5, 6
+        OFF_EXITED, OFF_NEXT, NEXT_STRIDE, OFF_NEXT_SEQ, SIZE = 0, 64, 192, 256, 288, 320, 352, 360, 364, 368, 376, 380, \
+        448, 128, 704, 768
+    OP_RESET, OP_SET_STATE, OP_SET_XI, OP_CONFIG, OP_EXIT, OP_AHEAD_STEP = 2, 3, 4, 5, 6, 8
 
     def __init__(self, device, noisy):
         import os
@@ -108,7 +110,7 @@ class _ResidentScalarCore:
         self.device = _device.require_cuda(device)
         self.lib = _lib.load()
         self.noisy = bool(noisy)
-        self._pin = t.zeros(512, dtype=t.uint8).pin_memory()               # renv_scalar_ctrl, device-mapped host memory
+        self._pin = t.zeros(1024, dtype=t.uint8).pin_memory()              # renv_scalar_ctrl, device-mapped host memory
         raw = self._pin.numpy()
         u32 = lambda off, n=1: raw[off:off + 4 * n].view(np.uint32)          # noqa: E731
         f64 = lambda off, n: raw[off:off + 8 * n].view(np.float64)           # noqa: E731
@@ -118,12 +120,25 @@ class _ResidentScalarCore:
         self.out_reward = f64(self.OFF_REWARD, 1)
         self.out_done = raw[self.OFF_DONE:self.OFF_DONE + 8].view(np.int32)         # done, beyond
         self.out_viol = u32(self.OFF_VIOL)
+        # look-ahead block: what step(0) / step(1) would return from the kernel's current state (renv_scalar_ctrl.next)
+        self.next_seq = u32(self.OFF_NEXT_SEQ)
+        nx = lambda a: self.OFF_NEXT + a * self.NEXT_STRIDE                   # noqa: E731
+        self.next_state = [f64(nx(a), 4) for a in (0, 1)]
+        self.next_obs = [f64(nx(a) + 32, 4) for a in (0, 1)]
+        self.next_reward = [f64(nx(a) + 64, 1) for a in (0, 1)]
+        self.next_done = [raw[nx(a) + 72:nx(a) + 80].view(np.int32) for a in (0, 1)]      # done, beyond
+        self.lookahead = os.environ.get("RENV_SCALAR_LOOKAHEAD", "1") != "0"
+        # the words the step path polls / writes, as plain Python ints (a memoryview item costs a third of a numpy one)
+        self._words = memoryview(raw).cast("B").cast("I")
+        self._raw = raw
+        self._unpack_outcome = struct.Struct("<4d4ddii").unpack_from     # state, obs, reward, done, beyond
+        self.obs_now = None                    # Noisy variant: the observation of the last step / reset
         with t.cuda.device(self.device):
             self._save = t.zeros(_lib.SCALAR_SAVE_BYTES, dtype=t.uint8, device=self.device)
             self._stream = t.cuda.Stream(device=self.device)
         self._ctrl_ptr, self._save_ptr = ctypes.c_void_p(self._pin.data_ptr()), ctypes.c_void_p(self._save.data_ptr())
         self._lease_ns = int(float(os.environ.get("RENV_SCALAR_LEASE_US", "300")) * 1000)
-        self._lease_id, self._running, self._seq = 0, False, 0
+        self._lease_id, self._running, self._seq, self._pending = 0, False, 0, False
         self.tick = 0
         self.state_tuple, self.xi_tuple, self.beyond = None, None, None
         self.config_key = None
@@ -139,23 +154,38 @@ class _ResidentScalarCore:
             raise _lib.RenvError("renv_cartpole_scalar_serve", rc, _lib.strerror(rc))
         self._running = True
 
-    def _call(self, op):
-        """Ring one request in and wait for its acknowledgement (bounded: relaunches an expired lease, raises after 5 s)."""
-        if not self._running or self.exited[0] == self._lease_id:
-            self._launch()
-        seq = self._seq = (self._seq + 1) & 0xFFFFFF
-        self.request[0] = (seq << 8) | op
-        ack, spins = self.ack, 0
-        while ack[0] != seq:
+    W_REQUEST, W_ACK, W_EXITED, W_NEXT_SEQ = OFF_REQUEST // 4, OFF_ACK // 4, OFF_EXITED // 4, OFF_NEXT_SEQ // 4
+
+    def _wait(self, word, seq):
+        """Spin until the kernel stored `seq` into 32-bit word `word` (W_ACK or W_NEXT_SEQ); bounded: relaunches an
+        expired lease (the new instance finds the request still pending), raises after ~5 s."""
+        w, spins = self._words, 0
+        while w[word] != seq:
             spins += 1
             if not spins & 0x3FF:                     # every 1024 polls (~50 us): did the lease expire under us?
-                if self.exited[0] == self._lease_id and ack[0] != seq:
-                    self._launch()                    # the new instance finds the request still pending
+                if w[self.W_EXITED] == self._lease_id and w[word] != seq:
+                    self._launch()
                 elif spins > 50_000_000:
                     raise RuntimeError("the resident scalar-env kernel did not answer request %d" % seq)
 
+    def _ring(self, op):
+        """Write one request word.  At most one request is outstanding: the caller has waited for the previous one."""
+        w = self._words
+        if not self._running or w[self.W_EXITED] == self._lease_id:
+            self._launch()
+        seq = self._seq = (self._seq + 1) & 0xFFFFFF
+        w[self.W_REQUEST] = (seq << 8) | op
+        return seq
+
+    def _call(self, op):
+        """Ring one request in and wait for its acknowledgement."""
+        if self._pending:                             # a look-ahead step is still in flight: let the kernel take it first
+            self._wait(self.W_NEXT_SEQ, self._seq)    # (look-ahead steps are not acknowledged, their successors are published)
+            self._pending = False
+        self._wait(self.W_ACK, self._ring(op))
+
     def close(self):
-        if self._running and self.exited[0] != self._lease_id:
+        if self._running and (self._pending or self.exited[0] != self._lease_id):
             try:
                 self._call(self.OP_EXIT)
             except Exception:  # noqa: BLE001
@@ -190,6 +220,8 @@ class _ResidentScalarCore:
                 a[9 + k] = dr_cfg.lb[k] if dr_type == _lib.DR_TRUNCNORM else (0.1 if dr_type == _lib.DR_GAUSSIAN else 0.0)
         u = self.arg_u64
         u[0], u[1], u[2], u[3] = int(seed) & 0xFFFFFFFFFFFFFFFF, 1 if integrator == _lib.EULER else 0, dr_type, int(self.noisy)
+        u[4] = self.tick                  # the kernel counts the step clock itself from here (look-ahead observations)
+        u[5] = int(self.lookahead)
         self._call(self.OP_CONFIG)
         self._fetch(True)
 
@@ -210,16 +242,35 @@ class _ResidentScalarCore:
         self._call(self.OP_RESET)
         self.tick += 1
         self._fetch(True)
+        if self.noisy:
+            self.obs_now = self.out_obs.copy()
         return int(self.out_viol[0])
 
     def step(self, action):
-        if self.noisy:
-            self.arg_u64[0] = self.tick
+        if self.lookahead:
+            # The kernel has published both outcomes of the next step from its current state (next_seq == the last
+            # request's seq once it has).  Take ours and ring the step in WITHOUT waiting for it: the PCIe round trip
+            # overlaps whatever the caller does before its next call.
+            seq = self._seq
+            if self._words[self.W_NEXT_SEQ] != seq:
+                self._wait(self.W_NEXT_SEQ, seq)
+            # next_seq == seq: the kernel has consumed request seq and next[action] is what this step returns
+            out = self._unpack_outcome(self._raw, self.OFF_NEXT + action * self.NEXT_STRIDE)
+            self._ring(self.OP_AHEAD_STEP + action)
+            self._pending = True
+            self.tick += 1
+            self.state_tuple = out[0:4]
+            self.beyond = None if out[10] < 0 else out[10]
+            if self.noisy:
+                self.obs_now = np.array(out[4:8])
+            return out[8], bool(out[9])
         self._call(action)
         self.tick += 1
         self.state_tuple = tuple(self.out_state.tolist())
         b = int(self.out_done[1])
         self.beyond = None if b < 0 else b
+        if self.noisy:
+            self.obs_now = self.out_obs.copy()
         return float(self.out_reward[0]), bool(self.out_done[0])
 
 
@@ -319,8 +370,7 @@ class RandomCartPoleEnv(RandomEnv):
             core.set_xi(xi)
 
     def step(self, action):
-        err_msg = "%r (%s) invalid" % (action, type(action))
-        assert self.action_space.contains(action), err_msg
+        assert self.action_space.contains(action), "%r (%s) invalid" % (action, type(action))   # :173-174
         if self.state is None:
             raise TypeError("cannot unpack non-iterable NoneType object")   # the reference's failure before reset()
         core = self._core
@@ -332,7 +382,7 @@ class RandomCartPoleEnv(RandomEnv):
             reward, done = core.step(int(action))
             self.state = core.state_tuple
             self.steps_beyond_done = core.beyond
-            observation = core.out_obs.copy() if self.noisy else np.array(self.state)
+            observation = core.obs_now if self.noisy else np.array(self.state)
         else:
             # host-visible attributes the user may have assigned (env.state = ..., set_task, steps_beyond_done): plain
             # stores into the mapped buffers, no upload
@@ -368,7 +418,7 @@ class RandomCartPoleEnv(RandomEnv):
                     raise Exception(GAUSSIAN_FAIL_MSG)
             self.state = core.state_tuple
             self.steps_beyond_done = None
-            return core.out_obs.copy() if self.noisy else np.array(self.state)
+            return core.obs_now if self.noisy else np.array(self.state)
         if resample:
             self.set_random_task()
         # s0 ~ U(-0.05, 0.05)^4 drawn by the reset kernel (Philox keyed by seed / tick)

@@ -432,3 +432,45 @@ def test_resident_scalar_env_equals_the_launch_per_step_path_and_sample_task(mon
         bad = random_envs.RandomCartPoleEnv()
         bad.set_dr_distribution("gaussian", [-5.0, 0.1, 1.0, 0.1, 0.1, 0.01, 0.5, 0.05]); bad.set_dr_training(True)
         bad.reset()
+
+
+@pytest.mark.parametrize("noisy", [False, True])
+def test_scalar_env_lookahead_equals_the_synchronous_protocol(monkeypatch, noisy):
+    """The resident kernel publishes both outcomes of the next step (renv_scalar_ctrl.next) and env.step returns one of
+    them without waiting for the round trip (RENV_SCALAR_LOOKAHEAD, default on).  The episodes equal those of the
+    synchronous request/acknowledge protocol bit for bit -- with resets, state / task / steps_beyond_done edits between
+    steps, stepping past `done`, a re-seed, and a lease that expires while a step is still in flight."""
+    import time
+
+    def run(lookahead):
+        monkeypatch.setenv("RENV_SCALAR_LOOKAHEAD", "1" if lookahead else "0")
+        monkeypatch.setenv("RENV_SCALAR_LEASE_US", "200")
+        env = random_envs.RandomCartPoleEnv(noisy=noisy)
+        assert env._core.lookahead is lookahead
+        env.seed(3)
+        env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True)
+        rs = np.random.RandomState(2)
+        out = [env.reset().copy(), env.get_task().copy()]
+        for k in range(400):
+            o, r, d, _ = env.step(int(rs.randint(2)))
+            out.append(np.concatenate([o, [r, float(d)], env.state, [-1 if env.steps_beyond_done is None else env.steps_beyond_done]]))
+            if d and k % 4 != 0:
+                out.append(env.reset().copy()); out.append(env.get_task().copy())
+            if k == 50:
+                env.state = (0.01, -0.02, 0.03, 0.04)                  # user-assigned state between two steps
+            if k == 90:
+                env.set_task(9.0, 1.2, 0.15, 0.45)
+            if k == 130:
+                env.kinematics_integrator = "semi-implicit"
+            if k == 170:
+                time.sleep(0.005)                                      # the lease expires with the last step in flight
+            if k == 200:
+                env.seed(3); out.append(env.reset().copy())            # re-seeding restarts the stream
+            if k == 260:
+                env.noise_level = 4e-4
+        env.close()
+        return out
+    a, b = run(True), run(False)
+    assert len(a) == len(b)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert np.array_equal(x, y), i
