@@ -22,6 +22,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--batches", type=int, default=4)
 ap.add_argument("--modes", default="chain,branches,eager,lone,big")
 ap.add_argument("--kernels", default="grid,tile,grid_lean,tile_lean")
+ap.add_argument("--tile-envs", type=int, default=0, help="envs per step CTA of the variant library (RENV_STEP_THREADS * 4)")
 args = ap.parse_args()
 if args.lib:
     os.environ["RENV_B200_LIB"] = os.path.abspath(args.lib)
@@ -30,6 +31,9 @@ import torch  # noqa: E402
 
 import random_envs_b200 as renv  # noqa: E402
 from random_envs_b200 import _device, _lib  # noqa: E402
+
+if args.tile_envs:
+    _lib.TILE_ENVS["float32"] = args.tile_envs      # sizes the `progress` array of the tile-ordered step
 
 SEARCH = [2.0, 20.0, 0.5, 3.0, 0.05, 0.3, 0.1, 1.0]
 dev = torch.device("cuda", 0)
