@@ -47,5 +47,28 @@ s.set_dr_distribution("fullgaussian", {"mean": np.full(30, 2.0), "cov": np.eye(3
 for n in (1, 63, 65, 1000):
     for dt in (torch.float32, torch.float64):
         s.sample_tasks_tensor(n, dtype=dt)
+# round 2: random-policy rollout across action-block boundaries, lean / tile-ordered step, flag bits on the host path,
+# the resident scalar env with and without look-ahead
+for n in (1, 33, 1031, 3 * 1024 + 5):
+    env = renv.RandomCartPoleVecEnv(n, seed=n, max_episode_steps=11)
+    env.set_dr_distribution("uniform", SEARCH); env.set_dr_training(True); env.reset()
+    for _ in range(125):
+        env.step(env.sample_actions())
+    env.rollout(None, 0.0, 140)
+    env.step_host(np.zeros(n, dtype=np.uint8)); env.step_host(np.ones(n, dtype=np.uint8))
+    lean = renv.RandomCartPoleVecEnv(n, seed=n, lean=True, tile_ordering=True)
+    lean.set_dr_distribution("uniform", SEARCH); lean.set_dr_training(True); lean.reset()
+    for _ in range(40):
+        lean.step(lean.sample_actions())
+for look in ("1", "0"):
+    os.environ["RENV_SCALAR_LOOKAHEAD"] = look
+    for noisy in (False, True):
+        e = renv.RandomCartPoleEnv(noisy=noisy)
+        e.seed(1); e.set_dr_distribution("uniform", SEARCH); e.set_dr_training(True); e.reset()
+        for k in range(300):
+            _, _, d, _ = e.step(k & 1)
+            if d:
+                e.reset()
+        e.close()
 torch.cuda.synchronize()
 print("sanitize driver done")

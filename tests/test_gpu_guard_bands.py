@@ -118,3 +118,19 @@ def test_sampler_kernels_stay_inside_their_buffers(dtype, dim):
             torch.cuda.synchronize()
             ar.check()
             assert bool((out > 0).all()), (dr_type, n, dim)       # every element was written
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4097])
+def test_pack_flags_stays_inside_its_buffers(n):
+    """renv_pack_flags_u8 writes exactly ceil(n / 32) words and reads nothing it may not (flags sized n rounded up to 4
+    bytes only): canaries around both buffers stay intact and flags past n never reach the bits."""
+    ar = Arena(1 << 16)
+    flags = ar.take((n + 3) // 4 * 4, torch.uint8)
+    bits = ar.take((n + 31) // 32 * 4, torch.int32)
+    flags.fill_(1)                                   # incl. the padding bytes past n
+    bits.zero_()
+    _lib.call("renv_pack_flags_u8", _device.ptr(flags), _device.ptr(bits), n, _device.stream_ptr(torch.device("cuda", 0)))
+    torch.cuda.synchronize()
+    ar.check()
+    got = np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little")
+    assert got[:n].all() and not got[n:].any()
