@@ -102,3 +102,30 @@ def test_noisy_and_rollout_argument_validation_without_a_gpu():
     assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 5, 0, 500, 0, None, 4100, None, None) == -2            # stats alignment
     cfg = _lib.make_dr_cfg("uniform", [0.0] * 5, [1.0] * 5)
     assert lib.renv_cartpole_rollout_f32(ctypes.byref(env), w, 0.0, 5, 0, 500, 0, ctypes.byref(cfg), 4096, None, None) == -4   # dim != 4
+
+
+def test_scalar_ctrl_offsets_in_python_match_the_header(tmp_path):
+    """random_cartpole._ResidentScalarCore addresses struct renv_scalar_ctrl by byte offset (the block is shared with a
+    running kernel through pinned host memory): the offsets must be the C compiler's."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    fields = ["request", "arg", "arg_u64", "state", "obs", "xi", "reward", "done", "beyond", "violations", "ack",
+              "exited", "next", "next_seq"]
+    src = tmp_path / "offsets.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "renv.h"\nint main(void) {\n' +
+                   "".join('  printf("%s %%zu\\n", offsetof(renv_scalar_ctrl, %s));\n' % (f, f) for f in fields) +
+                   '  printf("sizeof %zu\\n", sizeof(renv_scalar_ctrl));\n'
+                   '  printf("stride %zu\\n", sizeof(struct renv_scalar_outcome));\n'
+                   '  printf("outcome_reward %zu\\n", offsetof(struct renv_scalar_outcome, reward));\n  return 0;\n}\n')
+    exe = tmp_path / "offsets"
+    subprocess.run([gcc, "-I", os.path.dirname(HEADER), "-o", str(exe), str(src)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    from random_envs_b200.random_cartpole import _ResidentScalarCore as C
+    want = dict(request=C.OFF_REQUEST, arg=C.OFF_ARG, arg_u64=C.OFF_ARG_U64, state=C.OFF_STATE, obs=C.OFF_OBS, xi=C.OFF_XI,
+                reward=C.OFF_REWARD, done=C.OFF_DONE, beyond=C.OFF_BEYOND, violations=C.OFF_VIOL, ack=C.OFF_ACK,
+                exited=C.OFF_EXITED, next=C.OFF_NEXT, next_seq=C.OFF_NEXT_SEQ, sizeof=C.SIZE, stride=C.NEXT_STRIDE,
+                outcome_reward=64)
+    assert {k: int(v) for k, v in got.items()} == want
