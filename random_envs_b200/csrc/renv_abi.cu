@@ -2,6 +2,7 @@
 // Stateless and re-entrant: nothing is allocated, cached or synchronised here.
 #include "../../include/renv.h"
 #include "renv_kernels.cuh"
+#include <cmath>
 #include "renv_rollout_pair.cuh"
 #include "renv_fullgauss_tc.cuh"
 #include "renv_scalar_server.cuh"
@@ -129,6 +130,16 @@ template <int kType, int kStore>
 void launch_sampler(double *out, int64_t n, const DrCfgPrepared<double> &c, uint64_t seed, uint64_t sample_id0, uint32_t call,
                     unsigned long long *violations, int items, unsigned blocks, cudaStream_t st)
 {
+    if (kType == kDrUniform) {
+        // the fast loop pre-scales the widths by 2^-53: exact unless a width is subnormal-small or not finite
+        bool plain = true;
+        for (int k = 0; k < c.dim; ++k) plain = plain && (c.b[k] == 0.0 || (std::fabs(c.b[k]) > 1e-250 && std::isfinite(c.b[k])));
+        if (plain) {
+            const PhiloxKeys ks = philox_keys((uint32_t)seed, (uint32_t)(seed >> 32));
+            dr_sample_f64_uniform_kernel<kStore><<<blocks, kSampleThreads, 0, st>>>(out, n, c, ks, sample_id0, call, items);
+            return;
+        }
+    }
     dr_sample_kernel<double, kType, kStore><<<blocks, kSampleThreads, 0, st>>>(out, n, c, seed, sample_id0, call, violations, items);
 }
 

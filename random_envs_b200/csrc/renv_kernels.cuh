@@ -931,6 +931,60 @@ dr_sample_f32_kernel(float *__restrict__ out, int64_t n, const __grid_constant__
     if (kDrType == kDrGaussian && viol && violations) atomicAdd(violations, (unsigned long long)viol);
 }
 
+// The fp64 UNIFORM law on the same loop (what RandomEnv.sample_tasks() of the float64 drop-in API runs): one Philox block
+// = two doubles = 16 bytes, so the issue budget per byte is that of the fp32 kernel.  numpy's 53-bit recipe
+// u = ((hi >> 5) * 2^26 + (lo >> 6)) * 2^-53 is EXACT in every step (27- and 26-bit integers, powers of two), hence
+//   * the two int -> double conversions are an OR into the mantissa of 2^52 and one exact DADD each (I2F.F64 is a
+//     quarter-rate instruction),
+//   * m = fma(a, 2^26, b) is the exact 53-bit integer, and rn(width * u) == rn((width * 2^-53) * m): the product has
+//     the same real value, so low + width * u keeps numpy's two roundings with one DMUL and one DADD.
+// Bit-identical to dr_sample_kernel<double, kDrUniform> (tests/test_gpu_samplers.py compares both with the oracle).
+__device__ __forceinline__ double exact_u32_to_double(uint32_t v)          // v < 2^32: exact
+{
+    return __dadd_rn(__hiloint2double(0x43300000, (int)v), -4503599627370496.0);
+}
+template <int kStore>
+__global__ void __launch_bounds__(kSampleThreads, 3)
+dr_sample_f64_uniform_kernel(double *__restrict__ out, int64_t n, const __grid_constant__ DrCfgPrepared<double> cfg,
+                             const __grid_constant__ PhiloxKeys ks, uint64_t sample_id0, uint32_t call, int items)
+{
+    const int dim = cfg.dim;
+    const int kTile = tile_samples<double>(dim, items);
+    const int blocks_per_sample = (dim + 1) / 2;
+    int log2pad = 0;
+    while ((1 << log2pad) < blocks_per_sample) ++log2pad;
+    const int j = threadIdx.x & ((1 << log2pad) - 1);
+    const int lane_sample = threadIdx.x >> log2pad, samples_per_pass = kSampleThreads >> log2pad;
+    const int64_t first = (int64_t)blockIdx.x * kTile;
+    const int samples = (int)min((int64_t)kTile, n - first);
+    if (j >= blocks_per_sample || lane_sample >= samples) return;
+    const DimBlock<double> blk = load_dim_block(cfg, j);
+    const double w0 = blk.b[0] * (1.0 / 9007199254740992.0), w1 = blk.b[1] * (1.0 / 9007199254740992.0);   // exact
+    double *row = out + (first + lane_sample) * dim + j * 2;
+    const int64_t row_step = (int64_t)samples_per_pass * dim;
+    const uint64_t id0 = sample_id0 + (uint64_t)(first + lane_sample);
+    int todo = (samples - lane_sample + samples_per_pass - 1) / samples_per_pass;
+    const uint64_t to_wrap = (0x100000000ull - (id0 & 0xffffffffull) + (uint64_t)samples_per_pass - 1) / (uint64_t)samples_per_pass;
+    uint64_t id = id0;
+    while (todo > 0) {
+        const int seg = (int)min((uint64_t)todo, id == id0 ? to_wrap : (uint64_t)todo);    // a tile wraps at most once
+        const uint32_t c1 = (uint32_t)(id >> 32) & 0xffffu, c2 = call, c3 = ((uint32_t)kTasks << 24) | (uint32_t)j;
+        uint32_t c0 = (uint32_t)id;
+#pragma unroll 1
+        for (int k = seg; k > 0; --k) {
+            const uint4 r = philox4x32_10(make_uint4(c0, c1, c2, c3), ks);
+            const double m0 = fma(exact_u32_to_double(r.x >> 5), 67108864.0, exact_u32_to_double(r.y >> 6));
+            const double m1 = fma(exact_u32_to_double(r.z >> 5), 67108864.0, exact_u32_to_double(r.w >> 6));
+            double v[2] = { __dadd_rn(blk.a[0], __dmul_rn(w0, m0)), __dadd_rn(blk.a[1], __dmul_rn(w1, m1)) };
+            store_block<double, kStore>(row, v, blk.valid);
+            c0 += (uint32_t)samples_per_pass;
+            row += row_step;
+        }
+        id += (uint64_t)seg * (uint64_t)samples_per_pass;
+        todo -= seg;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // sample_tasks(n) for dr_type 'fullgaussian' (random_env.py:192-198): x = mean + F z, clip [0,4], denormalise
 // ------------------------------------------------------------------------------------------------

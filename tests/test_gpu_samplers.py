@@ -176,3 +176,27 @@ def test_every_env_of_the_suite_samples_inside_its_search_bounds(env_id):
     s.set_dr_distribution("truncnorm", _interleave(mid, (hi - lo) / 8))
     y = s.sample_tasks(513)
     assert np.all(np.abs(y - mid) <= (hi - lo) / 4 + 1e-12) and np.all(y >= np.array(table.lower_bounds))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("dr_type", ["uniform", "gaussian", "truncnorm"])
+def test_sample_ids_across_the_2_32_boundary(dr_type, dtype):
+    """The fast sampler loops keep Philox counter words 1..3 constant inside a 2^32-aligned segment of sample ids and
+    split a tile that crosses a multiple of 2^32.  One launch over ids [2^32 - 777, 2^32 + 4000) must equal the two
+    launches that stop / start at the boundary (neither of which crosses it), and, for the uniform law, the oracle."""
+    table = random_envs.XI_TABLES["RandomHumanoid-v0"]
+    lo = np.array([b[0] for b in table.search_bounds]); hi = np.array([b[1] for b in table.search_bounds])
+    a, b = (lo, hi) if dr_type == "uniform" else ((lo + hi) / 2, (hi - lo) / 10)
+    start = (1 << 32) - 777
+
+    def draw(n, id0):
+        s = _sampler("RandomHumanoid-v0", dr_type, a, b, seed=31)       # fresh sampler: call index 0 every time
+        return s.sample_tasks_tensor(n, dtype=dtype, sample_id0=id0).cpu().numpy()
+    whole = draw(4777, start)
+    assert np.array_equal(whole[:777], draw(777, start)) and np.array_equal(whole[777:], draw(4000, 1 << 32))
+    assert not np.array_equal(whole[777:1777], draw(1000, 0))          # the high id word is part of the key
+    if dr_type == "uniform":
+        npdt = np.float32 if dtype == torch.float32 else np.float64
+        for i in (0, 776, 777, 778, 4776):
+            assert np.array_equal(whole[i], c_oracle.xi_uniform(31, start + i, 0, lo, hi, purpose=c_oracle.PURPOSE_TASKS,
+                                                                dtype=npdt)), i
